@@ -1,0 +1,135 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU via ref_shim.
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python oracle/make_golden.py
+The fixtures are small (inputs, outputs, per-parameter gradient norms, parameter checksums); the parameters
+themselves are regenerated from the seed by nero_b200.params (bit-identical to the reference's initialisers,
+asserted here) plus oracle.perturb_params.
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+warnings.filterwarnings('ignore')
+
+import ref_shim  # noqa: E402
+import nero_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def npy(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def param_checksums(sd):
+    keys = sorted(k for k in sd if not k.endswith('FG_LUT'))
+    return np.array([[float(sd[k].double().sum()), float(sd[k].double().abs().sum())] for k in keys])
+
+
+def make_encoding_kats():
+    ref_shim.install()
+    from network.field import get_embedder, IPE, sample_pdf
+    from utils.ref_utils import generate_ide_fn
+    from utils.raw_utils import linear_to_srgb
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(64, 3, generator=g) * 2 - 1
+    x[0] = torch.tensor([0.1, 0.2, 0.3])
+    out = {'x': x}
+    for L in (4, 6, 8):
+        out[f'pe{L}'] = get_embedder(L, 3)[0](x)
+    x4 = torch.rand(32, 4, generator=g) * 2 - 1
+    out['x4'] = x4
+    out['pe10_4'] = get_embedder(10, 4)[0](x4)
+    ide = generate_ide_fn(5)
+    dirs = torch.nn.functional.normalize(torch.randn(96, 3, generator=g), dim=-1)
+    dirs[0] = torch.nn.functional.normalize(torch.tensor([1e-6, 1e-6, 1.0]), dim=-1)
+    dirs[1] = torch.tensor([1.0, 0.0, 0.0])
+    dirs[2] = torch.tensor([0.0, -1.0, 0.0])
+    kap = torch.rand(96, 1, generator=g)
+    kap[:8] = 0.0
+    kap[8:16] = 1.0
+    out.update(ide_dirs=dirs, ide_kappa=kap, ide=ide(dirs, kap))
+    mean = torch.randn(40, 2, generator=g)
+    var = torch.rand(40, 2, generator=g)
+    out.update(ipe_mean=mean, ipe_var=var, ipe=IPE(mean, var, 0, 6))
+    lin = torch.cat([torch.linspace(-0.1, 1.5, 200), torch.tensor([0.0031308, 0.0031307, 0.0031309])])
+    out.update(srgb_in=lin, srgb=linear_to_srgb(lin))
+    bins = torch.sort(torch.rand(24, 33, generator=g), -1)[0]
+    w = torch.rand(24, 32, generator=g) ** 4
+    w[0] = 0.0
+    out.update(pdf_bins=bins, pdf_w=w, pdf_out=sample_pdf(bins, w, 16, det=True))
+    np.savez_compressed(os.path.join(GOLD, 'kat_encodings.npz'), **npy(out))
+    print('kat_encodings', {k: tuple(v.shape) for k, v in out.items()})
+
+
+def make_shape_fixture(name, cfg, R, steps, seed=6033, pseed=7):
+    from nero_b200 import params as P  # product-side containers: must equal the reference's init
+    net = ref_shim.build_reference_shape_renderer(cfg, seed=seed)
+    sd_ref = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    mine = P.build_shape_state_dict(cfg, seed=seed)
+    assert list(mine.keys()) == list(sd_ref.keys())
+    assert all(torch.equal(mine[k], sd_ref[k]) for k in sd_ref), 'nero_b200.params init != reference init'
+    sd = O.perturb_params(sd_ref, seed=pseed)
+    net.load_state_dict(sd)
+    rays = O.synthetic_rays(R, seed=seed)
+    c = O.merged_cfg(cfg)
+    out = {'param_checksums': param_checksums(sd), 'R': R, 'seed': seed, 'pseed': pseed}
+    out.update({'in_' + k: v for k, v in rays.items()})
+    with torch.no_grad():
+        z = net.sample_ray(rays['rays_o'], rays['rays_d'], rays['near'], rays['far'], 0)
+    out['z_vals'] = z
+    # a perturbed-sampling variant with recorded draws (renderer.py:416,422 order)
+    torch.manual_seed(seed + 1)
+    with torch.no_grad():
+        zp = net.sample_ray(rays['rays_o'], rays['rays_d'], rays['near'], rays['far'], 1.0)
+    torch.manual_seed(seed + 1)
+    out['rand_inner'] = torch.rand([R, 1])
+    out['rand_bg'] = torch.rand([R, c['n_bg_samples']])
+    out['z_vals_perturbed'] = zp
+    names = [n for n, _ in net.named_parameters()]
+    for step in steps:
+        car = O.get_anneal_val(c, step)
+        net.zero_grad()
+        o = net.render_core(rays['rays_o'], rays['rays_d'], z, rays['human_poses'], cos_anneal_ratio=car, step=step,
+                            is_train=True)
+        loss = O.training_loss(o, rays['rgb'], c, step)
+        loss.backward()
+        pre = f's{step}_'
+        for k, v in o.items():
+            out[pre + k] = v
+        out[pre + 'loss'] = loss
+        out[pre + 'grad_norms'] = np.array([float(p.grad.double().norm()) if p.grad is not None else 0.0
+                                            for _, p in net.named_parameters()])
+        # a few full gradients (small tensors) for element-wise checks
+        gd = dict(net.named_parameters())
+        for k in ['deviation_network.variance', 'sdf_network.lin8.bias', 'sdf_network.lin0.weight_g',
+                  'color_network.albedo_predictor.6.weight_v', 'color_network.inner_weight.6.bias',
+                  'outer_nerf.rgb_linear.weight', 'sdf_network.lin4.weight_g']:
+            if gd[k].grad is not None:
+                out[pre + 'grad::' + k] = gd[k].grad.clone()
+    out['param_names'] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **npy(out))
+    print(name, 'saved; loss', {s: float(out[f's{s}_loss']) for s in steps},
+          'occ', {s: float(out[f's{s}_loss_occ'].mean()) for s in steps})
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    make_encoding_kats()
+    make_shape_fixture('shape_bell_r32', {'n_samples': 32, 'n_importance': 32}, 32, [500, 10000, 30000])
+    make_shape_fixture('shape_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}},
+                       24, [500, 30000])
+    make_shape_fixture('shape_bell_full_r16', {}, 16, [30000])
+
+
+if __name__ == '__main__':
+    main()
