@@ -1,0 +1,42 @@
+"""Shared test helpers: seeded parameters (product-side initialisers + oracle.perturb_params), fixtures."""
+import os
+import warnings
+
+import numpy as np
+import torch
+
+import nero_oracle as O
+from nero_b200 import params as P
+
+warnings.filterwarnings('ignore')
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz'), allow_pickle=False))
+
+
+def build_params(cfg, seed=6033, pseed=7, perturb=True):
+    sd = P.build_shape_state_dict(cfg, seed=seed)
+    return O.perturb_params(sd, seed=pseed) if perturb else sd
+
+
+def param_checksums(sd):
+    keys = sorted(k for k in sd if not k.endswith('FG_LUT'))
+    return np.array([[float(sd[k].double().sum()), float(sd[k].double().abs().sum())] for k in keys])
+
+
+def t(x, dtype=torch.float32):
+    return torch.from_numpy(np.asarray(x)).to(dtype)
+
+
+def rays_from_golden(g, dtype=torch.float32):
+    return {k[3:]: t(v, dtype) for k, v in g.items() if k.startswith('in_')}
+
+
+FIXTURE_CFGS = {
+    'shape_bell_r32': {'n_samples': 32, 'n_importance': 32},
+    'shape_bear_r24': {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}},
+    'shape_bell_full_r16': {},
+}
+FIXTURE_STEPS = {'shape_bell_r32': [500, 10000, 30000], 'shape_bear_r24': [500, 30000], 'shape_bell_full_r16': [30000]}
