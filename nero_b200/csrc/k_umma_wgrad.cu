@@ -1,0 +1,230 @@
+// tcgen05 weight-gradient kernel: dW[n, k] = sum_m dY[m, n] * X[m, k]  (+ sum_m dY2[m, n] * X2[m, k]).
+//
+// The contraction runs over SAMPLES (rows of both fp32 row-major inputs), so both tensor-core operands are
+// transposed on the fly: producer warps read columns of dY / X (coalesced across lanes), split to bf16 hi/lo
+// and write 8-sample k-chunks (one 16-byte store) into the same K-major SWIZZLE_128B layout the linear kernel
+// uses (tile row = feature index, K = sample index).  Split-K over CTAs: CTA p owns a contiguous range of
+// 64-sample chunks, accumulates a 128 x NW fp32 tile in TMEM and writes its partial to HBM; nero_wgrad_finish
+// (k_weights.cu) reduces the partials and applies the weight-norm chain rule.
+// The optional second pair implements the double-backward term of the SDF network,
+//   dW_k = abar_k^T h_k + v_k^T ubar_k      (SURVEY.md Appendix A.3, K4),
+// in ONE accumulator.  Column sums of dY (bias gradient) are produced by the dY producer threads for free.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nero {
+
+struct WgradParams {
+  const float* dY; int ldy; const float* X; int ldx;
+  const float* dY2; int ldy2; const float* X2; int ldx2;
+  int n0; int n_valid;   // output rows [n0, n0+128) = dY columns; columns >= n_valid read as zero
+  int k0; int k_valid;   // output cols [k0, k0+NW) = X columns; columns >= k_valid read as zero
+  float* partial; int ld_partial; int rows_partial;  // [P][rows_partial][ld_partial]
+  float* bias_partial;                               // [P][rows_partial] (may be null)
+  const int* m_ptr; int m_cap;
+};
+
+constexpr int WG_BM = 128, WG_BK = 64;
+constexpr int kWgThreads = 9 * 32;  // warps 0-3: dY producers + epilogue, 4-7: X producers, 8: MMA
+constexpr uint32_t kWgABytes = WG_BM * 128;
+
+template <int NW> struct WgCfg {
+  static constexpr uint32_t b_plane = NW * 128;
+  static constexpr uint32_t stage_bytes = 2 * kWgABytes + 2 * b_plane;
+  static constexpr int stages = (stage_bytes * 3 <= 200 * 1024) ? 3 : 2;
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 + 256;
+};
+
+// one thread transposes 8 consecutive samples of one column into a 16-byte k-chunk (hi and lo planes)
+__device__ __forceinline__ float produce_octet(const float* __restrict__ src, int ld, int col, bool col_ok, int s0, int M,
+                                               uint8_t* plane_hi, uint8_t* plane_lo, uint32_t row, uint32_t octet) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s = s0 + i;
+    x[i] = (col_ok && s < M) ? __ldg(src + size_t(s) * ld + col) : 0.0f;
+  }
+  uint32_t hw[4], lw[4];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(x[2 * i], h0, l0);
+    split_bf16(x[2 * i + 1], h1, l1);
+    __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+    hw[i] = *reinterpret_cast<uint32_t*>(&hh);
+    lw[i] = *reinterpret_cast<uint32_t*>(&ll);
+    sum += x[2 * i] + x[2 * i + 1];
+  }
+  const uint32_t off = row * 128u + ((octet ^ (row & 7u)) << 4);
+  *reinterpret_cast<uint4*>(plane_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *reinterpret_cast<uint4*>(plane_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  return sum;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradParams p) {
+  using Cfg = WgCfg<NW>;
+  constexpr int STAGES = Cfg::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int M = p.m_ptr ? *p.m_ptr : p.m_cap;
+  if (M > p.m_cap) M = p.m_cap;
+  const int P = gridDim.x;
+  const int total_chunks = (M + WG_BK - 1) / WG_BK;
+  const int cpp = (total_chunks + P - 1) / P;
+  const int c_begin = min(total_chunks, int(blockIdx.x) * cpp), c_end = min(total_chunks, c_begin + cpp);
+  const int npairs = p.dY2 ? 2 : 1;
+  const int nchunks = (c_end - c_begin) * npairs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<256>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    const bool is_a = warp < 4;
+    const int pw = warp & 3;
+    float bias_acc = 0.0f;
+    for (int g = 0; g < nchunks; ++g) {
+      const int s = g % STAGES;
+      const int pair = g / (c_end - c_begin);
+      const int chunk = c_begin + g % (c_end - c_begin);
+      const int s0 = chunk * WG_BK;
+      mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+      uint8_t* st = smem + s * Cfg::stage_bytes;
+      if (is_a) {
+        const float* src = pair ? p.dY2 : p.dY;
+        const int ld = pair ? p.ldy2 : p.ldy;
+        const uint32_t row = pw * 32 + lane;
+        const int col = p.n0 + int(row);
+        const bool ok = col < p.n_valid;
+        float sacc = 0.0f;
+#pragma unroll 2
+        for (int o = 0; o < 8; ++o) sacc += produce_octet(src, ld, col, ok, s0 + o * 8, M, st, st + kWgABytes, row, o);
+        if (pair == 0) bias_acc += sacc;
+      } else {
+        const float* src = pair ? p.X2 : p.X;
+        const int ld = pair ? p.ldx2 : p.ldx;
+        uint8_t* bh = st + 2 * kWgABytes;
+#pragma unroll 1
+        for (int j = 0; j < (NW + 127) / 128; ++j) {
+          const uint32_t row = j * 128 + pw * 32 + lane;
+          if (row < NW) {
+            const int col = p.k0 + int(row);
+            const bool ok = col < p.k_valid;
+#pragma unroll 2
+            for (int o = 0; o < 8; ++o) produce_octet(src, ld, col, ok, s0 + o * 8, M, bh, bh + Cfg::b_plane, row, o);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    if (is_a) {
+      // -------- epilogue: TMEM -> partial tile in HBM
+      mbar_wait(tfull, 0);
+      tcgen05_fence_after();
+      const int orow = p.n0 + pw * 32 + lane;
+      float* prow = p.partial + (size_t(blockIdx.x) * p.rows_partial + orow) * p.ld_partial + p.k0;
+      const uint32_t taddr = tmem_base + (uint32_t(pw * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < (NW + 31) / 32; ++cc) {
+        float v[32];
+        if (nchunks > 0) {
+          tmem_ld32(taddr + cc * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+        }
+        if (orow < p.rows_partial) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (cc * 32 + j < NW) *reinterpret_cast<float4*>(prow + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      if (p.bias_partial && p.k0 == 0 && orow < p.rows_partial)
+        p.bias_partial[size_t(blockIdx.x) * p.rows_partial + orow] = bias_acc;
+    }
+  } else {
+    // -------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(WG_BM, NW);
+    for (int g = 0; g < nchunks; ++g) {
+      const int s = g % STAGES;
+      mbar_wait(&full[s], (g / STAGES) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::stage_bytes);
+        const uint32_t a_lo = a_hi + kWgABytes;
+        const uint32_t b_hi = a_hi + 2 * kWgABytes;
+        const uint32_t b_lo = b_hi + Cfg::b_plane;
+#pragma unroll
+        for (int k = 0; k < WG_BK / 16; ++k) {
+          const uint64_t dah = make_desc_k_sw128(a_hi + k * 32), dal = make_desc_k_sw128(a_lo + k * 32);
+          const uint64_t dbh = make_desc_k_sw128(b_hi + k * 32), dbl = make_desc_k_sw128(b_lo + k * 32);
+          umma_bf16(tmem_base, dal, dbh, idesc, (g | k) != 0);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1);
+        }
+        umma_commit(&empty[s]);
+        if (g == nchunks - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+    }
+    if (nchunks == 0 && elect_one()) mbar_arrive(tfull);
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<256>(tmem_base);
+}
+
+template <int NW>
+static int launch_wgrad(const WgradParams& p, int P, cudaStream_t stream) {
+  using Cfg = WgCfg<NW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(umma_wgrad_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
+      return NERO_ERR_CUDA;
+    attr_set = true;
+  }
+  umma_wgrad_kernel<NW><<<P, kWgThreads, Cfg::smem_bytes, stream>>>(p);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
+// Computes partial[P][rows_partial][ld_partial] for output rows [0, n_rows_pad) and columns [0, k_pad)
+// (k_pad multiple of 64), decomposed into 128-row x {256,128,64}-column tiles.
+int wgrad_dispatch(WgradParams p, int n_rows_pad, int k_pad, int P, cudaStream_t stream) {
+  if ((p.ld_partial & 3) || k_pad % 64 || n_rows_pad % 16 || P <= 0) return NERO_ERR_ARG;
+  for (int n0 = 0; n0 < n_rows_pad; n0 += 128) {
+    int k0 = 0;
+    while (k0 < k_pad) {
+      const int rem = k_pad - k0;
+      p.n0 = n0; p.k0 = k0;
+      int rc;
+      if (rem >= 256) { rc = launch_wgrad<256>(p, P, stream); k0 += 256; }
+      else if (rem >= 128) { rc = launch_wgrad<128>(p, P, stream); k0 += 128; }
+      else { rc = launch_wgrad<64>(p, P, stream); k0 += 64; }
+      if (rc != NERO_OK) return rc;
+    }
+  }
+  return NERO_OK;
+}
+
+}  // namespace nero

@@ -1,0 +1,156 @@
+// Weight preparation (once per optimizer step) and weight-gradient finishing.
+//
+// nero_prep_weight: folds torch weight_norm (W = g * v / ||v||_row, network/field.py:118-119, 324-331) and
+// writes, for rows [row0, row0+nrows) of the layer,
+//   * img_f : the forward tensor-core operand image  (tile rows = output features, K = input layout columns)
+//   * img_t : the transposed image for input-gradient GEMMs (tile rows = input layout columns, K = output features)
+// both as split-bf16 (hi plane, lo plane) per 64-wide K chunk in the K-major SWIZZLE_128B shared-memory layout,
+// so the GEMM kernels fetch a chunk with one bulk copy.  `kmap` places reference input column k at column
+// kmap[k] of the (padded / re-ordered) activation layout the kernels actually use; `in_scale` folds constant
+// input scalings.  Images must be zero-initialised once (padding stays zero).
+//
+// nero_wgrad_finish: reduces the split-K partials of k_umma_wgrad.cu, maps layout columns back through kmap and
+// accumulates into .grad of (weight_g, weight_v, bias) via the weight-norm chain rule, or (weight, bias).
+#include "common.cuh"
+
+namespace nero {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.0f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+
+__device__ __forceinline__ void img_store(uint8_t* img, int rows_pad, int r, int kcol, float w) {
+  const int c = kcol >> 6, kk = kcol & 63;
+  uint8_t* base = img + size_t(c) * 2 * rows_pad * 128;
+  __nv_bfloat16 hi, lo;
+  split_bf16(w, hi, lo);
+  const uint32_t off = sw128_offset(r, kk);
+  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(base + size_t(rows_pad) * 128 + off) = lo;
+}
+
+__global__ void prep_weight_kernel(const float* __restrict__ v, const float* __restrict__ g, int K, int row0,
+                                   const int* __restrict__ kmap, float in_scale, uint8_t* img_f, int rows_pad_f,
+                                   uint8_t* img_t, int rows_pad_t, int t_c0, int t_ncols, float* w_eff, int ld_weff) {
+  __shared__ float sh[32];
+  const int r = blockIdx.x;       // local row
+  const int n = row0 + r;         // layer row
+  const float* vr = v + size_t(n) * K;
+  float scale = 1.0f;
+  if (g) {
+    float ss = 0.0f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) ss += vr[k] * vr[k];
+    ss = block_sum(ss, sh);
+    scale = g[n] / sqrtf(ss);
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float w = vr[k] * scale;            // same op order as torch._weight_norm: v * (g / ||v||)
+    if (w_eff) w_eff[size_t(n) * ld_weff + k] = w;
+    const int kc = kmap ? kmap[k] : k;
+    const float ws = w * in_scale;
+    if (img_f) img_store(img_f, rows_pad_f, r, kc, ws);
+    if (img_t && kc >= t_c0 && kc < t_c0 + t_ncols) img_store(img_t, rows_pad_t, kc - t_c0, r, ws);
+  }
+}
+
+int prep_weight(const float* v, const float* g, int K, int row0, int nrows, const int* kmap, float in_scale,
+                uint8_t* img_f, int rows_pad_f, uint8_t* img_t, int rows_pad_t, int t_c0, int t_ncols, float* w_eff,
+                int ld_weff, cudaStream_t stream) {
+  if (nrows <= 0) return NERO_OK;
+  prep_weight_kernel<<<nrows, 128, 0, stream>>>(v, g, K, row0, kmap, in_scale, img_f, rows_pad_f, img_t, rows_pad_t,
+                                                t_c0, t_ncols, w_eff, ld_weff);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
+// one block per layer row n = row0 + blockIdx.x
+__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
+                                    const float* __restrict__ bias_partial, int K, int row0,
+                                    const int* __restrict__ kmap, float in_scale, const float* __restrict__ v,
+                                    const float* __restrict__ g, float* grad_w, float* grad_g, float* grad_b,
+                                    const float* __restrict__ extra_row, float extra_scale) {
+  __shared__ float sh[32];
+  extern __shared__ float s_dw[];  // [K]
+  const int r = blockIdx.x, n = row0 + r;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int kc = kmap ? kmap[k] : k;
+    float acc = 0.0f;
+    for (int pidx = 0; pidx < P; ++pidx) acc += partial[(size_t(pidx) * rows_partial + r) * ld_partial + kc];
+    acc *= in_scale;
+    if (extra_row && r == 0) acc += extra_scale * extra_row[kc];
+    s_dw[k] = acc;
+  }
+  __syncthreads();
+  if (grad_b && bias_partial && threadIdx.x == 0) {
+    float b = 0.0f;
+    for (int pidx = 0; pidx < P; ++pidx) b += bias_partial[size_t(pidx) * rows_partial + r];
+    grad_b[n] += b;
+  }
+  if (g) {
+    const float* vr = v + size_t(n) * K;
+    float ss = 0.0f, dot = 0.0f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) { ss += vr[k] * vr[k]; dot += s_dw[k] * vr[k]; }
+    ss = block_sum(ss, sh);
+    dot = block_sum(dot, sh);
+    const float inv_norm = rsqrtf(ss);
+    const float dg = dot * inv_norm;                 // dL/dg = dW . v_hat
+    const float c = g[n] * inv_norm;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+      grad_w[size_t(n) * K + k] += c * (s_dw[k] - dg * vr[k] * inv_norm);
+    if (threadIdx.x == 0) grad_g[n] += dg;
+  } else {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) grad_w[size_t(n) * K + k] += s_dw[k];
+  }
+}
+
+int wgrad_finish(const float* partial, int P, int rows_partial, int ld_partial, const float* bias_partial, int K,
+                 int row0, int nrows, const int* kmap, float in_scale, const float* v, const float* g, float* grad_w,
+                 float* grad_g, float* grad_b, const float* extra_row, float extra_scale, cudaStream_t stream) {
+  if (nrows <= 0) return NERO_OK;
+  wgrad_finish_kernel<<<nrows, 128, K * sizeof(float), stream>>>(partial, P, rows_partial, ld_partial, bias_partial, K, row0,
+                                                                 kmap, in_scale, v, g, grad_w, grad_g, grad_b, extra_row,
+                                                                 extra_scale);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
+// column sums: out[j] (+)= sum_m w[m] * X[m, j]   (w may be null = ones).  Used for the sdf row of lin8:
+// dW8[0,:] = sum_m dsdf[m] * h8[m,:] + sum_m ubar8[m,:]   and for its bias.
+__global__ void colsum_kernel(const float* __restrict__ X, int ldx, int ncol, const float* __restrict__ w, int ldw,
+                              const int* __restrict__ m_ptr, int m_cap, float* out) {
+  int M = m_ptr ? *m_ptr : m_cap;
+  if (M > m_cap) M = m_cap;
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rlane = threadIdx.x >> 5;           // 8 row lanes
+  const int rows_per_block = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float acc = 0.0f;
+  if (col < ncol)
+    for (int r = r0 + rlane; r < r1; r += 8) acc += (w ? w[size_t(r) * ldw] : 1.0f) * X[size_t(r) * ldx + col];
+  __shared__ float sh[8][33];
+  sh[rlane][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rlane == 0 && col < ncol) {
+    float t = 0.0f;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x & 31];
+    atomicAdd(out + col, t);
+  }
+}
+
+int colsum(const float* X, int ldx, int ncol, const float* w, int ldw, const int* m_ptr, int m_cap, float* out,
+           cudaStream_t stream) {
+  if (m_cap <= 0 || ncol <= 0) return NERO_OK;
+  dim3 grid((ncol + 31) / 32, 64);
+  colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, ncol, w, ldw, m_ptr, m_cap, out);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
+}  // namespace nero

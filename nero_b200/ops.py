@@ -1,0 +1,271 @@
+"""ctypes bindings of libnero_b200.so + thin tensor-level wrappers.
+
+The product path has NO fallback: importing this module without the built library raises, and every wrapper
+launches a hand-written sm_100a kernel through the C ABI declared in include/nero_b200.h.
+
+NERO_DEBUG_GEMM=torch (tests only) swaps the tcgen05 GEMMs for an fp32 torch emulation OF THE SAME EPILOGUES so
+that test failures can be bisected between "GEMM kernel" and "everything else"; it is never enabled by the
+package itself and bench.py / smoke() refuse to run with it.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libnero_b200.so')
+
+ACT_NONE, ACT_SOFTPLUS100, ACT_RELU, ACT_SIGMOID, ACT_EXPCLAMP = 0, 1, 2, 3, 4
+EPI_BIAS_ACT, EPI_MUL_DACT, EPI_TANGENT = 0, 1, 2
+_NPADS = (16, 64, 128, 224, 256)
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(f'{_LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                      '(nero_b200 has no CPU or PyTorch fallback)')
+lib = ctypes.CDLL(_LIB_PATH)
+
+launch_count = 0  # kernels launched through the C ABI (bench.py reports it)
+DEBUG_GEMM = os.environ.get('NERO_DEBUG_GEMM', '')
+
+
+def _ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise RuntimeError(f'{name} failed with code {rc}')
+
+
+def npad_for(n):
+    for c in _NPADS:
+        if n <= c:
+            return c
+    raise ValueError(f'width {n} > 256 not supported by one UMMA tile')
+
+
+def ceil_div(a, b):
+    return (a + b - 1) // b
+
+
+class PreparedLayer:
+    """Tensor-core operand images of rows [row0,row0+nrows) of one linear layer, rebuilt by prep() whenever the
+    parameters change (once per optimizer step).
+
+    k_layout : width of the activation layout the layer reads (A operand columns actually touched)
+    kmap     : reference input column -> layout column (None = identity)
+    t_cols   : (c0, ncols) layout columns for which input gradients are needed (None = no dX image)
+    """
+
+    def __init__(self, weight, g, bias, device, row0=0, nrows=None, kmap=None, k_layout=None, t_cols=None):
+        self.weight, self.g, self.bias = weight, g, bias
+        N, K = weight.shape
+        self.K = K
+        self.row0 = row0
+        self.nrows = N - row0 if nrows is None else nrows
+        self.k_layout = k_layout if k_layout is not None else K
+        self.kmap_host = kmap
+        self.kmap = None if kmap is None else torch.tensor(kmap, dtype=torch.int32, device=device)
+        self.n_pad = npad_for(self.nrows)
+        self.k_chunks = ceil_div(self.k_layout, 64)
+        self.k_valid = ceil_div(self.k_layout, 4) * 4
+        self.img_f = torch.zeros(self.k_chunks * 2 * self.n_pad * 128, dtype=torch.uint8, device=device)
+        self.t_cols = t_cols
+        if t_cols is not None:
+            self.t_npad = npad_for(t_cols[1])
+            self.t_chunks = ceil_div(self.nrows, 64)
+            self.img_t = torch.zeros(self.t_chunks * 2 * self.t_npad * 128, dtype=torch.uint8, device=device)
+        else:
+            self.img_t = None
+        self.w_eff = torch.zeros(N, K, dtype=torch.float32, device=device)
+        self.bias_pad = torch.zeros(self.n_pad, dtype=torch.float32, device=device)
+
+    def prep(self):
+        global launch_count
+        w = self.weight.detach()
+        g = None if self.g is None else self.g.detach()
+        rc = lib.nero_prep_weight(_ptr(w), _ptr(g), self.K, self.row0, self.nrows, _ptr(self.kmap), ctypes.c_float(1.0),
+                                  _ptr(self.img_f), self.n_pad, _ptr(self.img_t), self.t_npad if self.img_t is not None else 0,
+                                  self.t_cols[0] if self.t_cols else 0, self.t_cols[1] if self.t_cols else 0,
+                                  _ptr(self.w_eff), self.K, _stream())
+        _check(rc, 'nero_prep_weight')
+        launch_count += 1
+        if self.bias is not None:
+            self.bias_pad[:self.nrows].copy_(self.bias.detach()[self.row0:self.row0 + self.nrows])
+
+    # fp32 layout-space weights for the debug emulation
+    def w_layout(self):
+        W = self.w_eff[self.row0:self.row0 + self.nrows]
+        if self.kmap is None and self.k_layout == self.K:
+            return W
+        out = torch.zeros(self.nrows, self.k_layout, device=W.device)
+        idx = self.kmap.long() if self.kmap is not None else torch.arange(self.K, device=W.device)
+        out[:, idx] = W
+        return out
+
+
+def _m_of(m_ptr, m_cap):
+    return m_cap if m_ptr is None else min(int(m_ptr.item()), m_cap)
+
+
+def _dact(h, dact):
+    if dact == ACT_SOFTPLUS100:
+        return torch.where(100 * h > 20, torch.ones_like(h), -torch.expm1(-100 * h))
+    if dact == ACT_RELU:
+        return (h > 0).float()
+    return torch.ones_like(h)
+
+
+def _act(x, act, p):
+    if act == ACT_SOFTPLUS100:
+        return torch.nn.functional.softplus(x, beta=100)
+    if act == ACT_RELU:
+        return torch.relu(x)
+    if act == ACT_SIGMOID:
+        return torch.sigmoid(x)
+    if act == ACT_EXPCLAMP:
+        return torch.exp(torch.clamp(x, max=p))
+    return x
+
+
+def view2d(t, col0, ld=None):
+    """(tensor, column offset) -> (data_ptr with offset, leading dimension)"""
+    return t, col0
+
+
+class Mat:
+    """A column window [c0, c0+ncol) of a 2-D fp32 row-major device buffer."""
+    __slots__ = ('t', 'c0', 'ncol')
+
+    def __init__(self, t, c0=0, ncol=None):
+        self.t, self.c0 = t, c0
+        self.ncol = t.shape[1] - c0 if ncol is None else ncol
+
+    @property
+    def ld(self):
+        return self.t.stride(0)
+
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr() + 4 * self.c0)
+
+    def view(self, m=None):
+        v = self.t[:, self.c0:self.c0 + self.ncol]
+        return v if m is None else v[:m]
+
+
+def linear(A: Mat, layer: PreparedLayer, out: Mat, ncol_out, *, transposed=False, mode=EPI_BIAS_ACT, act=ACT_NONE,
+           act_param=0.0, oscale=1.0, H: Mat = None, hscale=1.0, dact=ACT_NONE, V: Mat = None, out2: Mat = None,
+           addend: Mat = None, ncol_main=None, tail: Mat = None, m_ptr=None, m_cap=None, use_bias=True):
+    """out = epilogue(A @ W^T) (transposed=False) or epilogue(A @ W) restricted to t_cols (transposed=True)."""
+    global launch_count
+    if ncol_main is None:
+        ncol_main = ncol_out
+    if transposed:
+        img, n_pad, k_chunks, k_valid = layer.img_t, layer.t_npad, layer.t_chunks, ceil_div(layer.nrows, 4) * 4
+        bias = None
+    else:
+        img, n_pad, k_chunks, k_valid = layer.img_f, layer.n_pad, layer.k_chunks, layer.k_valid
+        bias = layer.bias_pad if (use_bias and layer.bias is not None) else None
+    if m_cap is None:
+        m_cap = A.t.shape[0]
+    if DEBUG_GEMM == 'torch':
+        return _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, oscale, H, hscale, dact, V, out2,
+                             addend, ncol_main, tail, m_ptr, m_cap, bias, k_valid)
+    rc = lib.nero_linear(A.ptr(), A.ld, k_valid, _ptr(img), n_pad, k_chunks, _ptr(bias), out.ptr(), out.ld, ncol_out,
+                         ctypes.c_float(oscale), mode, act, ctypes.c_float(act_param),
+                         H.ptr() if H else None, H.ld if H else 0, ctypes.c_float(hscale), dact,
+                         V.ptr() if V else None, V.ld if V else 0, out2.ptr() if out2 else None, out2.ld if out2 else 0,
+                         addend.ptr() if addend else None, addend.ld if addend else 0, ncol_main,
+                         tail.ptr() if tail else None, tail.ld if tail else 0, _ptr(m_ptr), m_cap, _stream())
+    _check(rc, 'nero_linear')
+    launch_count += 1
+
+
+def _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, oscale, H, hscale, dact, V, out2, addend,
+                  ncol_main, tail, m_ptr, m_cap, bias, k_valid):
+    M = _m_of(m_ptr, m_cap)
+    if M == 0:
+        return
+    Wl = layer.w_layout()                       # [nrows, k_layout]
+    if transposed:
+        c0, nc = layer.t_cols
+        a = A.t[:M, A.c0:A.c0 + layer.nrows]
+        acc = a @ Wl[:, c0:c0 + nc]             # [M, nc]
+    else:
+        a = A.t[:M, A.c0:A.c0 + layer.k_layout]
+        acc = a @ Wl.t()
+    acc = acc[:, :ncol_out]
+    if mode == EPI_BIAS_ACT:
+        if bias is not None:
+            acc = acc + bias[:ncol_out]
+        out.t[:M, out.c0:out.c0 + ncol_out] = oscale * _act(acc, act, act_param)
+        return
+    nm = min(ncol_main, ncol_out)
+    s = _dact(H.t[:M, H.c0:H.c0 + nm] * hscale, dact) if H is not None else torch.ones_like(acc[:, :nm])
+    r = oscale * s * acc[:, :nm]
+    if addend is not None:
+        r = r + addend.t[:M, addend.c0:addend.c0 + nm]
+    if mode == EPI_TANGENT:
+        out2.t[:M, out2.c0:out2.c0 + nm] = 100.0 * (1.0 - s) * V.t[:M, V.c0:V.c0 + nm] * acc[:, :nm]
+    out.t[:M, out.c0:out.c0 + nm] = r
+    if tail is not None and ncol_out > ncol_main:
+        tail.t[:M, tail.c0:tail.c0 + ncol_out - ncol_main] = oscale * acc[:, ncol_main:]
+
+
+class WgradWorkspace:
+    def __init__(self, device, P=64, rows=256, ld=384):
+        self.P, self.rows, self.ld = P, rows, ld
+        self.partial = torch.zeros(P, rows, ld, dtype=torch.float32, device=device)
+        self.bias_partial = torch.zeros(P, rows, dtype=torch.float32, device=device)
+
+
+def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: PreparedLayer, grad_w, grad_g, grad_b,
+          dY2: Mat = None, X2: Mat = None, m_ptr=None, m_cap=None, with_bias=True):
+    """Accumulate d(weight_g, weight_v, bias) (or d(weight, bias)) of rows [row0,row0+nrows) of `layer` from
+    dW_layout = dY^T X (+ dY2^T X2)."""
+    global launch_count
+    if m_cap is None:
+        m_cap = dY.t.shape[0]
+    n_rows_pad = ceil_div(n_valid, 16) * 16
+    k_pad = ceil_div(layer.k_layout, 64) * 64
+    assert k_pad <= ws.ld and n_rows_pad <= ws.rows
+    if DEBUG_GEMM == 'torch':
+        M = _m_of(m_ptr, m_cap)
+        dw = dY.t[:M, dY.c0:dY.c0 + n_valid].t() @ X.t[:M, X.c0:X.c0 + layer.k_layout]
+        if dY2 is not None:
+            dw = dw + dY2.t[:M, dY2.c0:dY2.c0 + n_valid].t() @ X2.t[:M, X2.c0:X2.c0 + layer.k_layout]
+        ws.partial.zero_()
+        ws.bias_partial.zero_()
+        ws.partial[0, :n_valid, :layer.k_layout] = dw
+        ws.bias_partial[0, :n_valid] = dY.t[:M, dY.c0:dY.c0 + n_valid].sum(0)
+    else:
+        P = ws.P
+        rc = lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
+                            dY2.ptr() if dY2 else None, dY2.ld if dY2 else 0, X2.ptr() if X2 else None, X2.ld if X2 else 0,
+                            _ptr(ws.partial), ws.ld, ws.rows, _ptr(ws.bias_partial), n_rows_pad, k_pad, P, _ptr(m_ptr),
+                            m_cap, _stream())
+        _check(rc, 'nero_wgrad')
+        launch_count += ceil_div(n_rows_pad, 128) * max(1, ceil_div(k_pad, 256))
+    g = None if layer.g is None else layer.g.detach()
+    rc = lib.nero_wgrad_finish(_ptr(ws.partial), ws.P, ws.rows, ws.ld, _ptr(ws.bias_partial) if with_bias else None,
+                               layer.K, layer.row0, layer.nrows, _ptr(layer.kmap), ctypes.c_float(1.0),
+                               _ptr(layer.weight.detach()), _ptr(g), _ptr(grad_w), _ptr(grad_g),
+                               _ptr(grad_b) if with_bias else None, None, ctypes.c_float(0.0), _stream())
+    _check(rc, 'nero_wgrad_finish')
+    launch_count += 1
+
+
+def colsum(X: Mat, ncol, out, w: Mat = None, m_ptr=None, m_cap=None):
+    global launch_count
+    if m_cap is None:
+        m_cap = X.t.shape[0]
+    rc = lib.nero_colsum(X.ptr(), X.ld, ncol, w.ptr() if w else None, w.ld if w else 0, _ptr(m_ptr), m_cap, _ptr(out),
+                         _stream())
+    _check(rc, 'nero_colsum')
+    launch_count += 1

@@ -1,0 +1,130 @@
+"""GPU parity of the tcgen05 GEMM kernels (nero_linear / nero_wgrad) against fp64 torch on the same inputs.
+Tolerance: the split-bf16 3-MMA scheme carries ~2^-17 relative error per product; we require
+max|err| <= 2e-5 * (|A| @ |W|^T) element-wise scale, i.e. far below the 1e-4 output tolerance of north_star."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_layer(ops, N, K, dev, wn=True, kmap=None, k_layout=None, t_cols=None, row0=0, nrows=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    v = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev)
+    gg = (1.0 + 0.1 * torch.randn(N, 1, generator=g)).to(dev) if wn else None
+    b = (0.1 * torch.randn(N, generator=g)).to(dev)
+    L = ops.PreparedLayer(v, gg, b, dev, row0=row0, nrows=nrows, kmap=kmap, k_layout=k_layout, t_cols=t_cols)
+    L.prep()
+    W = (gg * v / v.norm(dim=1, keepdim=True)) if wn else v
+    return L, W.double(), b.double()
+
+
+def _err(got, want, scale):
+    e = (got.double() - want).abs()
+    return float((e / (scale + 1e-30)).max()), float(e.max())
+
+
+@pytest.mark.parametrize('M,K,N,act', [(1000, 39, 256, 1), (4113, 256, 256, 1), (300, 256, 217, 1), (2500, 256, 1, 0),
+                                       (777, 256, 3, 3), (129, 72, 256, 2), (5000, 283, 128, 2), (40000, 256, 256, 2)])
+def test_linear_bias_act(M, K, N, act):
+    from nero_b200 import ops
+    dev = torch.device('cuda')
+    torch.manual_seed(M)
+    k_layout = K
+    L, W, b = _mk_layer(ops, N, K, dev, k_layout=k_layout)
+    lda = ops.ceil_div(K, 64) * 64 + 8
+    A = torch.randn(M + 5, lda, device=dev)
+    out = torch.full((M + 5, 264), -7.0, device=dev)
+    ops.linear(ops.Mat(A), L, ops.Mat(out, 4), N, act=act, act_param=0.0, m_cap=M)
+    torch.cuda.synchronize()
+    acc = A[:M, :K].double() @ W.t() + b
+    want = ops._act(acc, act, 0.0)
+    scale = A[:M, :K].double().abs() @ W.abs().t() + b.abs()
+    rel, ab = _err(out[:M, 4:4 + N], want, scale)
+    print(f'linear M={M} K={K} N={N} act={act}: rel {rel:.2e} abs {ab:.2e}')
+    assert rel < 2e-5
+    assert float(out[M:, :].min()) == -7.0 and float(out[:, :4].max()) == -7.0 and float(out[:, 4 + N:].max()) == -7.0
+
+
+def test_linear_kmap_and_device_count():
+    from nero_b200 import ops
+    dev = torch.device('cuda')
+    K, N, k_layout = 259, 256, 264
+    kmap = list(range(4, 260)) + [0, 1, 2]          # reference [feat(256), x(3)] -> layout [x(3), pad, feat...]
+    L, W, b = _mk_layer(ops, N, K, dev, kmap=kmap, k_layout=k_layout)
+    A = torch.randn(3000, 320, device=dev)
+    out = torch.zeros(3000, 256, device=dev)
+    mcount = torch.tensor([1234], dtype=torch.int32, device=dev)
+    ops.linear(ops.Mat(A), L, ops.Mat(out), N, act=2, m_ptr=mcount, m_cap=3000)
+    torch.cuda.synchronize()
+    Ar = A[:1234][:, kmap].double()
+    want = torch.relu(Ar @ W.t() + b)
+    rel, ab = _err(out[:1234], want, Ar.abs() @ W.abs().t() + 1)
+    print(f'kmap: rel {rel:.2e}')
+    assert rel < 2e-5 and float(out[1234:].abs().max()) == 0.0
+
+
+def test_linear_transposed_modes():
+    from nero_b200 import ops
+    dev = torch.device('cuda')
+    M, K, N = 2100, 256, 217
+    L, W, b = _mk_layer(ops, N, K, dev, t_cols=(0, 256))
+    dY = torch.randn(M, 224, device=dev)
+    H = torch.rand(M, 256, device=dev) * 0.05
+    V = torch.randn(M, 256, device=dev)
+    add = torch.randn(M, 256, device=dev)
+    out = torch.zeros(M, 256, device=dev)
+    out2 = torch.zeros(M, 256, device=dev)
+    tail = torch.zeros(M, 64, device=dev)
+    acc = dY[:, :N].double() @ W            # [M, 256]
+    s = ops._dact(H.double() * 1.4142135, 1)
+    scale = dY[:, :N].double().abs() @ W.abs()
+    # MUL_DACT with addend, tail split at 217
+    ops.linear(ops.Mat(dY), L, ops.Mat(out), 256, transposed=True, mode=ops.EPI_MUL_DACT, oscale=0.70710678, H=ops.Mat(H),
+               hscale=1.4142135, dact=1, addend=ops.Mat(add), ncol_main=217, tail=ops.Mat(tail))
+    torch.cuda.synchronize()
+    want = 0.70710678 * s[:, :217] * acc[:, :217] + add[:, :217].double()
+    rel, _ = _err(out[:, :217], want, scale[:, :217] + 1)
+    relt, _ = _err(tail[:, :39], 0.70710678 * acc[:, 217:], scale[:, 217:] + 1e-3)
+    print(f'mul_dact rel {rel:.2e} tail {relt:.2e}')
+    assert rel < 2e-5 and relt < 2e-5
+    # TANGENT
+    ops.linear(ops.Mat(dY), L, ops.Mat(out), 256, transposed=True, mode=ops.EPI_TANGENT, H=ops.Mat(H), hscale=1.0, dact=1,
+               V=ops.Mat(V), out2=ops.Mat(out2))
+    torch.cuda.synchronize()
+    s1 = ops._dact(H.double(), 1)
+    rel1, _ = _err(out, s1 * acc, scale + 1e-3)
+    rel2, _ = _err(out2, 100 * (1 - s1) * V.double() * acc, 100 * V.double().abs() * scale + 1e-3)
+    print(f'tangent rel {rel1:.2e} {rel2:.2e}')
+    assert rel1 < 2e-5 and rel2 < 2e-5
+
+
+@pytest.mark.parametrize('M,N,K,two', [(5000, 256, 256, False), (70001, 256, 256, True), (3000, 217, 256, False),
+                                       (999, 3, 259, False), (20000, 128, 283, False), (4000, 256, 39, True)])
+def test_wgrad(M, N, K, two):
+    from nero_b200 import ops
+    dev = torch.device('cuda')
+    L, W, b = _mk_layer(ops, N, K, dev)
+    ws = ops.WgradWorkspace(dev)
+    dY = torch.randn(M, 256 + 8, device=dev) * 0.1
+    X = torch.randn(M, 320, device=dev)
+    dY2 = torch.randn(M, 256, device=dev) * 0.1 if two else None
+    X2 = torch.randn(M, 320, device=dev) if two else None
+    gw, gg, gb = torch.zeros_like(L.weight), torch.zeros_like(L.g), torch.zeros(N, device=dev)
+    ops.wgrad(ws, ops.Mat(dY, 4), N, ops.Mat(X), L.k_valid, L, gw, gg, gb, ops.Mat(dY2) if two else None,
+              ops.Mat(X2) if two else None)
+    torch.cuda.synchronize()
+    # reference through autograd of weight norm in fp64
+    v = L.weight.double().requires_grad_(True)
+    g = L.g.double().requires_grad_(True)
+    Wd = g * v / v.norm(dim=1, keepdim=True)
+    dW = dY[:, 4:4 + N].double().t() @ X[:, :K].double()
+    if two:
+        dW = dW + dY2[:, :N].double().t() @ X2[:, :K].double()
+    (Wd * dW).sum().backward()
+    sc = float(dW.abs().max())
+    e_v = float((gw.double() - v.grad).abs().max()) / sc
+    e_g = float((gg.double() - g.grad).abs().max()) / sc
+    e_b = float((gb.double() - dY[:, 4:4 + N].double().sum(0)).abs().max()) / (float(dY.abs().sum(0).max()))
+    print(f'wgrad M={M} N={N} K={K}: v {e_v:.2e} g {e_g:.2e} b {e_b:.2e}')
+    assert e_v < 3e-5 and e_g < 3e-5 and e_b < 1e-5
