@@ -66,6 +66,75 @@ int nero_wgrad_finish(const float* partial, int P, int rows_partial, int ld_part
 int nero_colsum(const float* X, int ldx, int ncol, const float* w, int ldw, const int* m_ptr, int m_cap, float* out,
                 void* stream);
 
+/* ---- encodings --------------------------------------------------------------------------------------------
+ * Upload the IDE coefficient table mat[17][36] (HOST pointer; fp32-rounded like utils/ref_utils.py:77-82). */
+int nero_set_ide_table(const float* mat17x36_host);
+
+/* ---- render_core sample bookkeeping (network/renderer.py:554-572) -----------------------------------------
+ * ray_prepare: per-ray inner/outer counts + exclusive scan -> off_in/off_out, totals n_in/n_out (device ints).
+ * ray_fill: ordered compaction; writes slot[R,S] (inner i >= 0, outer -1-io), pts[i]=(x,y,z,dist), ray ids,
+ * PE6(p) rows (X0, and /sqrt2 into H4[:,217:256] for the skip concat of field.py:139-140), p into Y8[:,256:259],
+ * PE10([p/|p|,1/|p|]) rows (XN and H5[:, :84]), PE4(-dir) into FV[:,256:283], dist_out. */
+int nero_ray_prepare(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, int* cnt_in, int* cnt_out,
+                     int* off_in, int* off_out, int* n_in, int* n_out, void* stream);
+int nero_ray_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, const int* off_in, const int* off_out,
+                  int* slot, float* pts, int* ray_in, float* X0, int ld_x0, float* Y8, int ld_y8, float* H4, int ld_h4,
+                  float* XN, int ld_xn, float* H5, int ld_h5, float* FV, int ld_fv, float* dist_out, int* ray_out, void* stream);
+
+/* ---- analytic SDF gradient helpers (SDFNetwork.gradient, network/field.py:155-167) ------------------------- */
+int nero_dact_times_row(const float* H, int ldh, const float* row, float* V, int ldv, int ncol, const int* m_ptr, int m_cap, void* stream);
+int nero_pe_grad(const float* X0, int ldx, const float* U0, int ldu, const float* US, int lds, float* G, const int* m_ptr, int m_cap, void* stream);
+int nero_pe_tangent(const float* X0, int ldx, const float* DG, float* UB0, int ld0, float* UB4, int ld4, const int* m_ptr, int m_cap, void* stream);
+
+/* ---- NeuS SDF -> alpha + eikonal term (compute_sdf_alpha, network/renderer.py:484-512, :574) ---------------- */
+int nero_sdf_alpha_fwd(const float* Y8, int ldy, int sdf_col, const float* G, const float* pts, const int* ray_in, const float* rays_d,
+                       const float* variance, float car, float* alpha, float* gerr, const int* m_ptr, int m_cap, void* stream);
+int nero_sdf_alpha_bwd(const float* Y8, int ldy, int sdf_col, const float* G, const float* pts, const int* ray_in, const float* rays_d,
+                       const float* variance, float car, const float* dalpha, const float* dgerr, float* dY8, int lddy, float* DG,
+                       float* d_inv_s, const int* m_ptr, int m_cap, void* stream);
+
+/* ---- outer NeRF activations (compute_density_alpha, network/renderer.py:346-347, 514-520) ------------------- */
+int nero_nerf_post_fwd(const float* dens, int ldd, const float* rgb, int ldr, const float* dist, float* alpha, float* color,
+                       const int* m_ptr, int m_cap, void* stream);
+int nero_nerf_post_bwd(const float* dens, int ldd, const float* rgb, int ldr, const float* dist, const float* dalpha, const float* dcolor,
+                       float* ddens, int lddd, float* drgb, int lddr, const int* m_ptr, int m_cap, void* stream);
+
+/* ---- alpha compositing, warp per ray (network/renderer.py:578-579) ------------------------------------------ */
+int nero_composite_fwd(const int* slot, int R, int S, const float* a_in, const float* c_in, const float* a_out, const float* c_out,
+                       float* rgb, float* weights, void* stream);
+int nero_composite_bwd(const int* slot, int R, int S, const float* a_in, const float* c_in, const float* a_out, const float* c_out,
+                       const float* drgb, float* da_in, float* dc_in, float* da_out, float* dc_out, void* stream);
+
+/* ---- split-sum shading (AppShadingNetwork.forward, network/field.py:591-651; IDE utils/ref_utils.py:85-115) - */
+int nero_shade_prep_fwd(const float* G, const float* pts, const int* ray_in, const float* rays_d, const float* OUTS, float* E, int lde,
+                        float* GEO, const float* human_poses, float* EH, int ldeh, int pos_freq, const int* m_ptr, int m_cap, void* stream);
+int nero_shade_prep_bwd(const float* G, const float* pts, const int* ray_in, const float* rays_d, const float* OUTS, const float* GEO,
+                        const float* dE_dir, int ld_dir, const float* dE_inn, int ld_inn, const float* dE_dif, int ld_dif,
+                        const float* dEH, int ld_eh, const float* human_poses, const float* dNoV, float* DOUTS, float* DG,
+                        const int* m_ptr, int m_cap, void* stream);
+int nero_shade_combine_fwd(const float* OUTS, const float* GEO, const float* lut, float exp_max, int human, float* color,
+                           float* occ_prob, float* refl, const int* m_ptr, int m_cap, void* stream);
+int nero_shade_combine_bwd(const float* OUTS, const float* GEO, const float* lut, float exp_max, int human, const float* dcolor,
+                           const float* docc, float* DOUTS, float* dNoV, const int* m_ptr, int m_cap, void* stream);
+
+/* ---- NeuS hierarchical sampling (sample_ray / upsample / cat_z_vals, network/renderer.py:355-443;
+ *      sample_pdf network/field.py:399-429) and the occlusion march (get_weights/get_intersection, field.py:432-484) */
+int nero_sample_init(const float* rays_o, const float* rays_d, const float* near, const float* far, int R, int n, int nb,
+                     const float* lin_inner, const float* bg_base, const float* bg_lower, const float* bg_upper,
+                     const float* rand_inner, const float* rand_bg, float* z, int ldz, float* z_bg, int ldzb,
+                     float* X0, int ldx, float* HC, int ldh, void* stream);
+int nero_upsample(const float* rays_o, const float* rays_d, int R, const float* z, int ldz, const float* sdf, int lds, int n, int n_new,
+                  const float* variance, float inv_s_cap, int clip, int surface_variant, float* new_z, int ldn,
+                  float* X0, int ldx, float* HC, int ldh, float* wsum, void* stream);
+int nero_merge_samples(const float* z, int ldz, const float* sdf, int lds, int n, const float* nz, int ldn, const float* nsdf, int ldns,
+                       int m, float* oz, int ldoz, float* osdf, int ldos, int R, void* stream);
+int nero_occ_init(const float* pts, const float* refl, const int* sel, const int* p_ptr, int p_cap, int sn0, const float* lin,
+                  float* o_out, float* d_out, float* z, int ldz, float* X0, int ldx, float* HC, int ldh, void* stream);
+int nero_occ_select(const float* pts, const float* Y8, int ldy, int sdf_col, const float* G, const int* ray_in, const float* rays_d,
+                    float sdf_thresh, const int* m_ptr, int m_cap, int* sel, int* count, void* stream);
+int nero_occ_loss(const float* occ_prob, const float* gt, const int* sel, const int* p_ptr, int p_cap, float* loss_sum, float* docc_sign,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
