@@ -46,7 +46,7 @@ int nero_prep_weight(const float* v, const float* g, int K, int row0, int nrows,
  *   mode BIAS_ACT : out = oscale * act(acc + bias)
  *   mode MUL_DACT : out[:, :ncol_main] = oscale * act'(H*hscale) * acc (+ addend);  tail[:, :] = oscale * acc[:, ncol_main:]
  *   mode TANGENT  : as MUL_DACT, plus out2 = 100 * (1 - act'(H*hscale)) * V * acc   (softplus'' term)       */
-int nero_linear(const float* A, int lda, int k_valid, const void* wimg, int n_pad, int k_chunks, const float* bias,
+int nero_linear(const float* A, int lda, int k_valid, const void* wimg, int n_pad, int k_chunks, const float* bias, int n_bias,
                 float* out, int ldo, int ncol_out, float oscale, int mode, int act, float act_param,
                 const float* H, int ldh, float hscale, int dact, const float* V, int ldv, float* out2, int ldo2,
                 const float* addend, int ldadd, int ncol_main, float* tail, int ldt,

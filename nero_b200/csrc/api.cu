@@ -6,7 +6,7 @@ namespace nero {
 struct LinearParams {
   const float* A; int lda; int k_valid;
   const uint8_t* wimg; int n_pad; int k_chunks;
-  const float* bias;
+  const float* bias; int n_bias;
   float* out; int ldo; int ncol_out; float oscale;
   int mode; int act; float act_param;
   const float* H; int ldh; float hscale; int dact;
@@ -133,12 +133,12 @@ int nero_prep_weight(const float* v, const float* g, int K, int row0, int nrows,
                      w_eff, ld_weff, (cudaStream_t)stream);
 }
 
-int nero_linear(const float* A, int lda, int k_valid, const void* wimg, int n_pad, int k_chunks, const float* bias,
+int nero_linear(const float* A, int lda, int k_valid, const void* wimg, int n_pad, int k_chunks, const float* bias, int n_bias,
                 float* out, int ldo, int ncol_out, float oscale, int mode, int act, float act_param,
                 const float* H, int ldh, float hscale, int dact, const float* V, int ldv, float* out2, int ldo2,
                 const float* addend, int ldadd, int ncol_main, float* tail, int ldt,
                 const int* m_ptr, int m_cap, void* stream) {
-  LinearParams p{A, lda, k_valid, (const uint8_t*)wimg, n_pad, k_chunks, bias, out, ldo, ncol_out, oscale, mode, act, act_param,
+  LinearParams p{A, lda, k_valid, (const uint8_t*)wimg, n_pad, k_chunks, bias, n_bias, out, ldo, ncol_out, oscale, mode, act, act_param,
                  H, ldh, hscale, dact, V, ldv, out2, ldo2, addend, ldadd, ncol_main, tail, ldt, m_ptr, m_cap};
   if (!A || !wimg || !out || ncol_out > n_pad) return NERO_ERR_ARG;
   return linear_dispatch(p, (cudaStream_t)stream);

@@ -23,7 +23,7 @@ namespace nero {
 struct LinearParams {
   const float* A; int lda; int k_valid;
   const uint8_t* wimg; int n_pad; int k_chunks;
-  const float* bias;
+  const float* bias; int n_bias;
   float* out; int ldo; int ncol_out; float oscale;
   int mode; int act; float act_param;
   const float* H; int ldh; float hscale; int dact;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
     fence_mbar_init();
   }
   if (warp == kEpiWarps + kProdWarps + 1) tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.0f;
+  for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_bias) ? p.bias[i] : 0.0f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();

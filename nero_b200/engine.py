@@ -1,0 +1,578 @@
+"""Host-side orchestration of the stage-I hot path on one B200: sample_ray + render_core forward / backward.
+
+Python only sequences kernels: every arithmetic step is a hand-written sm_100a kernel reached through the C ABI
+(ops.K / ops.linear / ops.wgrad).  Data-dependent sizes (number of inner / outer samples) stay on the device:
+workspaces are sized for the worst case and kernels read the live counts from device memory.
+
+Reference call graph being replaced (paths relative to /root/reference):
+  NeROShapeRenderer.sample_ray   network/renderer.py:403-443  -> ShapeEngine.sample_ray
+  NeROShapeRenderer.render_core  network/renderer.py:550-606  -> ShapeEngine.render_core_forward / _backward
+  SDFNetwork.forward/.gradient   network/field.py:130-167     -> SdfNet.forward_with_gradient (+ tangent/backward sweeps)
+  AppShadingNetwork.forward      network/field.py:591-651     -> ShapeEngine._shade_forward / _shade_backward
+  NeRFNetwork.forward            network/field.py:258-283     -> NerfNet.forward / backward
+  compute_occ_loss/get_intersection  renderer.py:522-548, field.py:432-484 -> ShapeEngine._occ_forward
+Buffer layouts are documented in DESIGN.md section 3.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import Mat, K, linear, wgrad, ACT_NONE, ACT_SOFTPLUS100, ACT_RELU, ACT_SIGMOID, ACT_EXPCLAMP, EPI_MUL_DACT, EPI_TANGENT
+
+INV_SQRT2 = 0.7071067811865476
+SQRT2 = 1.4142135623730951
+# E buffer columns (k_shade.cu)
+E_PE6R, E_PE8X, E_IDER, E_IDEN, E_LD = 0, 40, 92, 164, 240
+# OUTS buffer columns
+O_MET, O_ROUGH, O_ALB, O_LD, O_LDIR, O_LI, O_IW, O_HUM, O_LDIM = 0, 4, 8, 12, 16, 20, 24, 28, 32
+Y8_LD, Y8_X, Y8_SDF = 320, 256, 260
+
+
+def ide_coefficient_table():
+    """mat[17,36] of Ref-NeRF's integrated directional encoding (eq. 6-8 of arXiv:2112.03907), computed in float64
+    and rounded to float32 exactly like utils/ref_utils.py:77-82 does before using it."""
+    def gbc(a, k):
+        return np.prod(a - np.arange(k)) / math.factorial(k)
+
+    def alc(l, m, k):
+        return ((-1) ** m * 2 ** l * math.factorial(l) / math.factorial(k) / math.factorial(l - k - m) *
+                gbc(0.5 * (l + k + m - 1.0), l))
+
+    def shc(l, m, k):
+        return np.sqrt((2.0 * l + 1.0) * math.factorial(l - m) / (4.0 * np.pi * math.factorial(l + m))) * alc(l, m, k)
+
+    cols = [(m, 2 ** e) for e in range(5) for m in range(2 ** e + 1)]
+    mat = np.zeros((17, len(cols)))
+    for i, (m, l) in enumerate(cols):
+        for k in range(l - m + 1):
+            mat[k, i] = shc(l, m, k)
+    return np.ascontiguousarray(mat.astype(np.float32))
+
+
+_ide_uploaded = False
+
+
+def upload_ide_table():
+    global _ide_uploaded
+    if not _ide_uploaded:
+        mat = ide_coefficient_table()
+        if not ops.DRY_RUN:
+            rc = ops.lib.nero_set_ide_table(mat.ctypes.data_as(ops.ctypes.c_void_p))
+            ops._check(rc, 'nero_set_ide_table')
+        _ide_uploaded = True
+
+
+class Grads:
+    """Maps parameters to their .grad buffers; missing grads become views of ONE flat zeroed buffer (the buffer a
+    data-parallel run all-reduces with a single NCCL call)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        self.total = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def ensure(self):
+        if any(p.grad is None for p in self.params):
+            self.flat = torch.zeros(self.total, dtype=torch.float32, device=self.params[0].device)
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                if p.grad is None:
+                    p.grad = self.flat[off:off + n].view_as(p)
+                off += n
+        return self.flat
+
+
+class Predictor:
+    """make_predictor (network/field.py:310-346): 4 weight-normed linears, ReLU x3, final activation."""
+
+    def __init__(self, pp, dev, n_out, act, act_param=0.0, kmap=None, k_layout=None, t_cols=None):
+        ls = pp.layers()
+        self.n_out, self.act, self.act_param = n_out, act, act_param
+        self.layers = [ops.PreparedLayer(ls[0].weight_v, ls[0].weight_g, ls[0].bias, dev, kmap=kmap, k_layout=k_layout, t_cols=t_cols)]
+        for l in ls[1:]:
+            self.layers.append(ops.PreparedLayer(l.weight_v, l.weight_g, l.bias, dev, t_cols=(0, 256)))
+        self.pl = ls
+
+    def prep(self):
+        for l in self.layers:
+            l.prep()
+
+    def forward(self, A, acts, out, m_ptr, m_cap):
+        L = self.layers
+        linear(A, L[0], Mat(acts[0]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
+        linear(Mat(acts[0]), L[1], Mat(acts[1]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
+        linear(Mat(acts[1]), L[2], Mat(acts[2]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
+        linear(Mat(acts[2]), L[3], out, self.n_out, act=self.act, act_param=self.act_param, m_ptr=m_ptr, m_cap=m_cap)
+
+    def backward(self, ws, dpre, A, acts, dHa, dHb, m_ptr, m_cap, dX=None, dx_ncol=0, dx_addend=None):
+        """dpre: Mat over the pre-activation gradient of the output (n_out columns)."""
+        L, P = self.layers, self.pl
+        g = lambda i: (P[i].weight_v.grad, P[i].weight_g.grad, P[i].bias.grad)
+        kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        linear(dpre, L[3], Mat(dHa), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(acts[2]), dact=ACT_RELU, **kw)
+        wgrad(ws, dpre, self.n_out, Mat(acts[2]), 256, L[3], *g(3), **kw)
+        linear(Mat(dHa), L[2], Mat(dHb), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(acts[1]), dact=ACT_RELU, **kw)
+        wgrad(ws, Mat(dHa), 256, Mat(acts[1]), 256, L[2], *g(2), **kw)
+        linear(Mat(dHb), L[1], Mat(dHa), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(acts[0]), dact=ACT_RELU, **kw)
+        wgrad(ws, Mat(dHb), 256, Mat(acts[0]), 256, L[1], *g(1), **kw)
+        if dX is not None:
+            linear(Mat(dHa), L[0], dX, dx_ncol, transposed=True, mode=EPI_MUL_DACT, addend=dx_addend, **kw)
+        wgrad(ws, Mat(dHa), 256, A, L[0].k_valid, L[0], *g(0), **kw)
+
+
+class SdfNet:
+    """SDFNetwork (network/field.py:60-181): PE6 -> 8 x softplus(beta=100) hidden layers (skip concat before layer 4) -> 257."""
+
+    def __init__(self, sp, dev):
+        self.sp = sp
+        ls = sp.layers()
+        assert len(ls) == 9 and sp.multires == 6 and tuple(sp.skip_in) == (4,), 'kernels are laid out for the default SDF network'
+        self.L = []
+        for k, l in enumerate(ls[:8]):
+            tc = (0, 39) if k == 0 else (0, 256)
+            self.L.append(ops.PreparedLayer(l.weight_v, l.weight_g, l.bias, dev, t_cols=tc))
+        l8 = ls[8]
+        self.L8f = ops.PreparedLayer(l8.weight_v, l8.weight_g, l8.bias, dev, row0=1, nrows=256, t_cols=(0, 256))   # feature rows
+        self.L8s = ops.PreparedLayer(l8.weight_v, l8.weight_g, l8.bias, dev, row0=0, nrows=1, t_cols=(0, 256))     # sdf row
+        self.nout = [256, 256, 256, 217, 256, 256, 256, 256]
+        self.tmp_row = torch.zeros(256, device=dev)
+        self.tmp_b = torch.zeros(4, device=dev)
+
+    def prep(self):
+        for l in self.L + [self.L8f, self.L8s]:
+            l.prep()
+
+    def hidden_forward(self, X0, Hs, H4buf, m_ptr, m_cap):
+        """X0 [.,64] -> Hs[k] = input of layer k+1 (k = 0..7); the output of lin3 goes into H4buf[:, :217] scaled by
+        1/sqrt2 next to the pre-filled PE/sqrt2 tail (skip concat, field.py:139-140)."""
+        kw = dict(act=ACT_SOFTPLUS100, m_ptr=m_ptr, m_cap=m_cap)
+        linear(Mat(X0), self.L[0], Mat(Hs[0]), 256, **kw)
+        linear(Mat(Hs[0]), self.L[1], Mat(Hs[1]), 256, **kw)
+        linear(Mat(Hs[1]), self.L[2], Mat(Hs[2]), 256, **kw)
+        linear(Mat(Hs[2]), self.L[3], Mat(H4buf), 217, oscale=INV_SQRT2, **kw)
+        linear(Mat(H4buf), self.L[4], Mat(Hs[4]), 256, **kw)
+        linear(Mat(Hs[4]), self.L[5], Mat(Hs[5]), 256, **kw)
+        linear(Mat(Hs[5]), self.L[6], Mat(Hs[6]), 256, **kw)
+        linear(Mat(Hs[6]), self.L[7], Mat(Hs[7]), 256, **kw)
+
+    def sdf_only(self, X0, SA, SB, SC, out, m_ptr, m_cap):
+        """Forward-only SDF value (sampling / occlusion march): hidden stack in 3 rotating buffers, last layer row 0 only."""
+        Hs = [SA, SB, SA, SC, SA, SB, SA, SB]
+        self.hidden_forward(X0, Hs, SC, m_ptr, m_cap)
+        linear(Mat(SB), self.L8s, Mat(out), 1, m_ptr=m_ptr, m_cap=m_cap)
+
+    # ---- training path on the compacted inner samples --------------------------------------------------
+    def forward_with_gradient(self, w, m_ptr, m_cap):
+        H = w['H']   # H[1..8]; H[4] has the PE/sqrt2 tail pre-filled by ray_fill
+        Hs = [H[1], H[2], H[3], H[4], H[5], H[6], H[7], H[8]]
+        self.hidden_forward(w['X0'], Hs, H[4], m_ptr, m_cap)
+        kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        linear(Mat(H[8]), self.L8f, Mat(w['Y8']), 256, **kw)                 # feature vector -> Y8[:, 0:256]
+        linear(Mat(H[8]), self.L8s, Mat(w['Y8'], Y8_SDF), 1, **kw)          # sdf -> Y8[:, 260]
+        # reverse sweep for d sdf / d x  (v_k = sigma_k * u_{k+1}, u_k = W_k^T v_k)
+        V = w['V']
+        K('nero_dact_times_row', H[8], 256, self.L8s.w_eff, V[7], 256, 256, m_ptr, m_cap)
+        for k in range(7, 0, -1):
+            if k == 4:   # u_4 = [217 -> v_3 (through 1/sqrt2) | 39 -> skip branch to the PE input]
+                linear(Mat(V[4]), self.L[4], Mat(V[3]), 256, transposed=True, mode=EPI_MUL_DACT, oscale=INV_SQRT2, H=Mat(H[4]),
+                       hscale=SQRT2, dact=ACT_SOFTPLUS100, ncol_main=217, tail=Mat(w['USKIP']), **kw)
+            else:
+                linear(Mat(V[k]), self.L[k], Mat(V[k - 1]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[k]),
+                       dact=ACT_SOFTPLUS100, **kw)
+        linear(Mat(V[0]), self.L[0], Mat(w['U0']), 39, transposed=True, mode=EPI_MUL_DACT, **kw)
+        K('nero_pe_grad', w['X0'], 64, w['U0'], 64, w['USKIP'], 64, w['G'], m_ptr, m_cap)
+
+    def backward(self, ws, w, m_ptr, m_cap, grads_of):
+        """Given dY8 (feature cols 0..255, sdf col 260) and DG (d loss / d gradient), accumulate all SDF parameter grads."""
+        H, V, UB, AB = w['H'], w['V'], w['UB'], w['ABAR']
+        kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        # tangent sweep (adjoint of the reverse sweep): ubar_0 = J_PE dg ; vbar_k = W_k ubar_k ; ubar_{k+1} = sigma_k vbar_k
+        K('nero_pe_tangent', w['X0'], 64, w['DG'], UB[0], 64, UB[4], 256, m_ptr, m_cap)
+        for k in range(8):
+            A = Mat(UB[0]) if k == 0 else Mat(UB[k])
+            if k == 3:
+                linear(A, self.L[3], Mat(UB[4]), 217, use_bias=False, mode=EPI_TANGENT, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2,
+                       dact=ACT_SOFTPLUS100, V=Mat(V[3]), out2=Mat(AB[3]), **kw)
+            else:
+                linear(A, self.L[k], Mat(UB[k + 1]), 256, use_bias=False, mode=EPI_TANGENT, H=Mat(H[k + 1]), dact=ACT_SOFTPLUS100,
+                       V=Mat(V[k]), out2=Mat(AB[k]), **kw)
+        # value backward: abar_7 = sigma_7 * (W8^T ybar) + q_7 ; abar_{k-1} = sigma_{k-1} * (W_k^T abar_k) + q_{k-1}
+        dY8 = w['dY8']
+        linear(Mat(dY8), self.L8f, Mat(AB[7]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[8]), dact=ACT_SOFTPLUS100,
+               addend=Mat(AB[7]), **kw)
+        linear(Mat(dY8, Y8_SDF), self.L8s, Mat(AB[7]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[8]), dact=ACT_SOFTPLUS100,
+               addend=Mat(AB[7]), **kw)
+        for k in range(7, 0, -1):
+            if k == 4:
+                linear(Mat(AB[4]), self.L[4], Mat(AB[3]), 217, transposed=True, mode=EPI_MUL_DACT, oscale=INV_SQRT2, H=Mat(H[4]),
+                       hscale=SQRT2, dact=ACT_SOFTPLUS100, addend=Mat(AB[3]), **kw)
+            else:
+                linear(Mat(AB[k]), self.L[k], Mat(AB[k - 1]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[k]),
+                       dact=ACT_SOFTPLUS100, addend=Mat(AB[k - 1]), **kw)
+        # weight gradients: dW_k = abar_k^T h_k + v_k^T ubar_k
+        ls = self.sp.layers()
+        for k in range(8):
+            Hin = Mat(w['X0']) if k == 0 else Mat(H[k])
+            Uin = Mat(UB[0]) if k == 0 else Mat(UB[k])
+            wgrad(ws, Mat(AB[k]), self.nout[k], Hin, self.L[k].k_valid, self.L[k], ls[k].weight_v.grad, ls[k].weight_g.grad,
+                  ls[k].bias.grad, dY2=Mat(V[k]), X2=Uin, **kw)
+        l8 = ls[8]
+        wgrad(ws, Mat(dY8), 256, Mat(H[8]), 256, self.L8f, l8.weight_v.grad, l8.weight_g.grad, l8.bias.grad, **kw)
+        # sdf row: dW8[0,:] = sum_m dsdf[m] h8[m,:] + sum_m ubar_8[m,:] ; db8[0] = sum dsdf
+        self.tmp_row.zero_()
+        self.tmp_b.zero_()
+        ops.colsum(Mat(H[8]), 256, self.tmp_row, w=Mat(dY8, Y8_SDF), m_ptr=m_ptr, m_cap=m_cap)
+        ops.colsum(Mat(UB[8]), 256, self.tmp_row, m_ptr=m_ptr, m_cap=m_cap)
+        ops.colsum(Mat(dY8, Y8_SDF), 1, self.tmp_b, m_ptr=m_ptr, m_cap=m_cap)
+        K('nero_wgrad_finish', self.tmp_row, 1, 1, 256, self.tmp_b, 256, 0, 1, None, 1.0, l8.weight_v.detach(), l8.weight_g.detach(),
+          l8.weight_v.grad, l8.weight_g.grad, l8.bias.grad, None, 0.0)
+
+    def value_backward(self, ws, w, Hs, X0, dsdf, m_ptr, m_cap, AB):
+        """Backward of a value-only pass (sdf output only; used for the step<1000 sdf regulariser)."""
+        raise NotImplementedError
+
+
+class NerfNet:
+    """Outer NeRF++ (NeRFNetwork, network/field.py:205-297): PE10(4-d) -> 8 x ReLU(256) with skip, density head,
+    feature + PE4(view) -> 128 -> rgb."""
+
+    def __init__(self, npar, dev):
+        self.np = npar
+        pl = npar.pts_linears
+        mk = lambda l, **kw: ops.PreparedLayer(l.weight, None, l.bias, dev, **kw)
+        self.P = [mk(pl[0])] + [mk(pl[i], t_cols=(0, 256)) for i in range(1, 5)] + [mk(pl[5], t_cols=(84, 256))] + \
+                 [mk(pl[i], t_cols=(0, 256)) for i in (6, 7)]
+        self.alpha = mk(npar.alpha_linear, t_cols=(0, 256))
+        self.feature = mk(npar.feature_linear, t_cols=(0, 256))
+        self.views = mk(npar.views_linears[0], t_cols=(0, 256))
+        self.rgb = mk(npar.rgb_linear, t_cols=(0, 128))
+
+    def all_layers(self):
+        return self.P + [self.alpha, self.feature, self.views, self.rgb]
+
+    def prep(self):
+        for l in self.all_layers():
+            l.prep()
+
+    def forward(self, w, m_ptr, m_cap):
+        kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        N = w['NH']
+        linear(Mat(w['XN']), self.P[0], Mat(N[1]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[1]), self.P[1], Mat(N[2]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[2]), self.P[2], Mat(N[3]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[3]), self.P[3], Mat(N[4]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[4]), self.P[4], Mat(w['H5'], 84), 256, act=ACT_RELU, **kw)    # cat([input_pts, h]) (field.py:268-269)
+        linear(Mat(w['H5']), self.P[5], Mat(N[6]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[6]), self.P[6], Mat(N[7]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[7]), self.P[7], Mat(N[8]), 256, act=ACT_RELU, **kw)
+        linear(Mat(N[8]), self.alpha, Mat(w['DENS']), 1, **kw)
+        linear(Mat(N[8]), self.feature, Mat(w['FV']), 256, **kw)
+        linear(Mat(w['FV']), self.views, Mat(w['HV']), 128, act=ACT_RELU, **kw)
+        linear(Mat(w['HV']), self.rgb, Mat(w['RGBRAW']), 3, **kw)
+
+    def backward(self, ws, w, m_ptr, m_cap):
+        kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        N, dA, dB = w['NH'], w['dNa'], w['dNb']
+        n = self.np
+        gp = lambda l: (l.weight.grad, None, l.bias.grad)
+        R = dict(transposed=True, mode=EPI_MUL_DACT, dact=ACT_RELU)
+        linear(Mat(w['dRGBRAW']), self.rgb, Mat(w['dHV']), 128, H=Mat(w['HV']), **R, **kw)
+        wgrad(ws, Mat(w['dRGBRAW']), 3, Mat(w['HV']), 128, self.rgb, *gp(n.rgb_linear), **kw)
+        linear(Mat(w['dHV']), self.views, Mat(w['dFV']), 256, transposed=True, mode=EPI_MUL_DACT, **kw)
+        wgrad(ws, Mat(w['dHV']), 128, Mat(w['FV']), self.views.k_valid, self.views, *gp(n.views_linears[0]), **kw)
+        linear(Mat(w['dFV']), self.feature, Mat(dA), 256, H=Mat(N[8]), **R, **kw)
+        linear(Mat(w['dDENS']), self.alpha, Mat(dA), 256, H=Mat(N[8]), addend=Mat(dA), **R, **kw)
+        wgrad(ws, Mat(w['dFV']), 256, Mat(N[8]), 256, self.feature, *gp(n.feature_linear), **kw)
+        wgrad(ws, Mat(w['dDENS']), 1, Mat(N[8]), 256, self.alpha, *gp(n.alpha_linear), **kw)
+        pl = n.pts_linears
+        linear(Mat(dA), self.P[7], Mat(dB), 256, H=Mat(N[7]), **R, **kw)
+        wgrad(ws, Mat(dA), 256, Mat(N[7]), 256, self.P[7], *gp(pl[7]), **kw)
+        linear(Mat(dB), self.P[6], Mat(dA), 256, H=Mat(N[6]), **R, **kw)
+        wgrad(ws, Mat(dB), 256, Mat(N[6]), 256, self.P[6], *gp(pl[6]), **kw)
+        linear(Mat(dA), self.P[5], Mat(dB), 256, H=Mat(w['H5'], 84), **R, **kw)
+        wgrad(ws, Mat(dA), 256, Mat(w['H5']), self.P[5].k_valid, self.P[5], *gp(pl[5]), **kw)
+        linear(Mat(dB), self.P[4], Mat(dA), 256, H=Mat(N[4]), **R, **kw)
+        wgrad(ws, Mat(dB), 256, Mat(N[4]), 256, self.P[4], *gp(pl[4]), **kw)
+        linear(Mat(dA), self.P[3], Mat(dB), 256, H=Mat(N[3]), **R, **kw)
+        wgrad(ws, Mat(dA), 256, Mat(N[3]), 256, self.P[3], *gp(pl[3]), **kw)
+        linear(Mat(dB), self.P[2], Mat(dA), 256, H=Mat(N[2]), **R, **kw)
+        wgrad(ws, Mat(dB), 256, Mat(N[2]), 256, self.P[2], *gp(pl[2]), **kw)
+        linear(Mat(dA), self.P[1], Mat(dB), 256, H=Mat(N[1]), **R, **kw)
+        wgrad(ws, Mat(dA), 256, Mat(N[1]), 256, self.P[1], *gp(pl[1]), **kw)
+        wgrad(ws, Mat(dB), 256, Mat(w['XN']), self.P[0].k_valid, self.P[0], *gp(pl[0]), **kw)
+
+
+class ShapeEngine:
+    def __init__(self, params, cfg):
+        """params: nero_b200.params.ShapeParams on a CUDA device; cfg: merged renderer cfg."""
+        self.p = params
+        self.cfg = cfg
+        self.scfg = params.color_network.cfg
+        dev = params.deviation_network.variance.device
+        assert dev.type == 'cuda' or ops.DRY_RUN, 'nero_b200 runs on a CUDA device only (no CPU fallback)'
+        self.dev = dev
+        if self.scfg['sphere_direction']:
+            raise NotImplementedError('sphere_direction=True is not implemented in the B200 path')
+        if self.scfg['light_pos_freq'] != 8:
+            raise NotImplementedError('light_pos_freq != 8')
+        upload_ide_table()
+        self.human = bool(self.scfg['human_light'])
+        self.exp_max = float(self.scfg['light_exp_max'])
+        c = params.color_network
+        self.sdf = SdfNet(params.sdf_network, dev)
+        self.nerf = NerfNet(params.outer_nerf, dev)
+        self.m_met = Predictor(c.metallic_predictor, dev, 1, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
+        self.m_rough = Predictor(c.roughness_predictor, dev, 1, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
+        self.m_alb = Predictor(c.albedo_predictor, dev, 3, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
+        self.m_outer = Predictor(c.outer_light, dev, 3, ACT_EXPCLAMP, self.exp_max, k_layout=72, t_cols=(0, 72))
+        self.m_inner = Predictor(c.inner_light, dev, 3, ACT_EXPCLAMP, self.exp_max,
+                                 kmap=list(range(51)) + [52 + i for i in range(72)], k_layout=124, t_cols=(52, 72))
+        self.m_iw = Predictor(c.inner_weight, dev, 1, ACT_NONE, kmap=[40 + i for i in range(51)] + list(range(39)), k_layout=91)
+        self.m_human = Predictor(c.human_light_predictor, dev, 4, ACT_EXPCLAMP, 0.0, k_layout=24, t_cols=(0, 24)) if self.human else None
+        self.lut = c.FG_LUT
+        self.grads = Grads(list(params.parameters()))
+        self.ws = ops.WgradWorkspace(dev)
+        self.w = None
+        self.cap = (0, 0)
+        n, nb = cfg['n_samples'], cfg['n_bg_samples']
+        # constant tables evaluated by torch on the CPU exactly like renderer.py:411-421
+        zo = torch.linspace(1e-3, 1.0 - 1.0 / (nb + 1.0), nb)
+        mids = .5 * (zo[1:] + zo[:-1])
+        self.t_lin = torch.linspace(0.0, 1.0, n).to(dev)
+        self.t_bg = zo.to(dev)
+        self.t_bg_lo = torch.cat([zo[:1], mids]).to(dev)
+        self.t_bg_hi = torch.cat([mids, zo[-1:]]).to(dev)
+        self.t_lin64 = torch.linspace(0, 1, 64).to(dev)
+        self.prepared_version = None
+
+    # ------------------------------------------------------------------ weights
+    def predictors(self):
+        ps = [self.m_met, self.m_rough, self.m_alb, self.m_outer, self.m_inner, self.m_iw]
+        return ps + ([self.m_human] if self.human else [])
+
+    def prepare_weights(self):
+        self.sdf.prep()
+        self.nerf.prep()
+        for m in self.predictors():
+            m.prep()
+
+    # ------------------------------------------------------------------ workspaces
+    def _alloc(self, R, S):
+        if self.cap == (R, S):
+            return
+        dev = self.dev
+        cap = R * S
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        w = {}
+        ns = self.cfg['n_samples']
+        caps = max(R * ns, self.cfg['occ_loss_max_pn'] * 64)
+        w.update(SX0=z(caps, 64), SA=z(caps, 256), SB=z(caps, 256), SC=z(caps, 256), SSDF=z(caps, 1),
+                 ZA=z(R, 128), ZB=z(R, 128), SDFA=z(R, 128), SDFB=z(R, 128), NEWZ=z(R, 32))
+        w.update(cnt_in=z(R, dt=torch.int32), cnt_out=z(R, dt=torch.int32), off_in=z(R, dt=torch.int32), off_out=z(R, dt=torch.int32),
+                 n_in=z(1, dt=torch.int32), n_out=z(1, dt=torch.int32), slot=z(R, S, dt=torch.int32))
+        # inner
+        w.update(X0=z(cap, 64), PTS=z(cap, 4), RAY_IN=z(cap, dt=torch.int32), Y8=z(cap, Y8_LD), U0=z(cap, 64), USKIP=z(cap, 64),
+                 G=z(cap, 4), OUTS=z(cap, O_LDIM), E=z(cap, E_LD), GEO=z(cap, 8), EH=z(cap, 64), COLOR_IN=z(cap, 4), OCCP=z(cap),
+                 REFL=z(cap, 4), ALPHA_IN=z(cap), GERR=z(cap))
+        w['H'] = [None] + [z(cap, 256) for _ in range(8)]
+        w['V'] = [z(cap, 256) for _ in range(8)]
+        names = ['met', 'rough', 'alb', 'odir', 'odif', 'inner', 'iw'] + (['human'] if self.human else [])
+        w['ACT'] = {k: [z(cap, 256) for _ in range(3)] for k in names}
+        # outer
+        w.update(XN=z(cap, 128), H5=z(cap, 384), DENS=z(cap, 4), FV=z(cap, 320), HV=z(cap, 128), RGBRAW=z(cap, 4), DIST_OUT=z(cap),
+                 RAY_OUT=z(cap, dt=torch.int32), ALPHA_OUT=z(cap), COLOR_OUT=z(cap, 4))
+        w['NH'] = [None] + [z(cap, 256) for _ in range(4)] + [None] + [z(cap, 256) for _ in range(3)]
+        # occlusion march
+        P = self.cfg['occ_loss_max_pn']
+        w.update(SEL=z(cap, dt=torch.int32), OCC_COUNT=z(1, dt=torch.int32), OCC_O=z(P, 3), OCC_D=z(P, 3), OCC_Z=z(P, 64),
+                 OCC_NEWZ=z(P, 16), OCC_GT=z(P), OCC_LOSS=z(1), DOCC=z(cap))
+        self.w = w
+        self.cap = (R, S)
+        self.bw_ready = False
+
+    def _alloc_backward(self):
+        if self.bw_ready:
+            return
+        R, S = self.cap
+        cap = R * S
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
+        w = self.w
+        w.update(dALPHA_IN=z(cap), dCOLOR_IN=z(cap, 4), DOUTS=z(cap, O_LDIM), DNOV=z(cap), dE_dir=z(cap, 128), dE_inn=z(cap, 128),
+                 dE_dif=z(cap, 128), dEH=z(cap, 64), DG=z(cap, 4), dY8=z(cap, Y8_LD), dHa=z(cap, 256), dHb=z(cap, 256),
+                 D_INV_S=z(1))
+        w['UB'] = [z(cap, 64)] + [z(cap, 256) for _ in range(8)]
+        w['ABAR'] = [z(cap, 256) for _ in range(8)]
+        w.update(dALPHA_OUT=z(cap), dCOLOR_OUT=z(cap, 4), dDENS=z(cap, 4), dRGBRAW=z(cap, 4), dHV=z(cap, 128), dFV=z(cap, 256),
+                 dNa=z(cap, 256), dNb=z(cap, 256))
+        self.bw_ready = True
+
+    # ------------------------------------------------------------------ sampling (renderer.py:403-443)
+    def sample_ray(self, rays_o, rays_d, near, far, rand_inner=None, rand_bg=None):
+        cfg = self.cfg
+        R = rays_o.shape[0]
+        n, nb, nimp, steps = cfg['n_samples'], cfg['n_bg_samples'], cfg['n_importance'], cfg['up_sample_steps']
+        S = n + nimp + nb
+        nn_ = nimp // steps
+        assert nimp % steps == 0 and nn_ <= 32 and n + nimp <= 128 and nb <= n, 'sampling kernels: <=32 new samples / step, <=128 inner samples'
+        self._alloc(R, S)
+        w = self.w
+        z_vals = torch.empty(R, S, device=self.dev)
+        var = self.p.deviation_network.variance.detach()
+        K('nero_sample_init', rays_o, rays_d, near, far, R, n, nb, self.t_lin, self.t_bg, self.t_bg_lo, self.t_bg_hi,
+          rand_inner, rand_bg, w['ZA'], 128, Mat(z_vals, n + nimp), S, w['SX0'], 64, w['SC'], 256)
+        self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, R * n)
+        cur_z, cur_sdf, lds = w['ZA'], w['SSDF'], n
+        nxt_z, nxt_sdf = w['ZB'], w['SDFB']
+        cur_n = n
+        for i in range(steps):
+            last = i + 1 == steps
+            K('nero_upsample', rays_o, rays_d, R, cur_z, 128, cur_sdf, lds, cur_n, nn_, var, float(64 * 2 ** i),
+              1 if cfg['clip_sample_variance'] else 0, 0, w['NEWZ'], 32, None if last else w['SX0'], 64,
+              None if last else w['SC'], 256, None)
+            if last:
+                K('nero_merge_samples', cur_z, 128, None, 0, cur_n, w['NEWZ'], 32, None, 0, nn_, z_vals, S, None, 0, R)
+            else:
+                self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, R * nn_)
+                K('nero_merge_samples', cur_z, 128, cur_sdf, lds, cur_n, w['NEWZ'], 32, w['SSDF'], nn_, nn_, nxt_z, 128, nxt_sdf, 128, R)
+                cur_z, nxt_z = nxt_z, (w['ZA'] if nxt_z is w['ZB'] else w['ZB'])
+                cur_sdf, nxt_sdf = nxt_sdf, (w['SDFA'] if nxt_sdf is w['SDFB'] else w['SDFB'])
+                lds = 128
+            cur_n += nn_
+        return z_vals
+
+    # ------------------------------------------------------------------ render_core forward (renderer.py:550-606)
+    def render_core_forward(self, rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio, step, perm=None):
+        cfg = self.cfg
+        R, S = z_vals.shape
+        self._alloc(R, S)
+        w = self.w
+        cap = R * S
+        var = self.p.deviation_network.variance.detach()
+        K('nero_ray_prepare', rays_o, rays_d, z_vals, R, S, w['cnt_in'], w['cnt_out'], w['off_in'], w['off_out'], w['n_in'], w['n_out'])
+        K('nero_ray_fill', rays_o, rays_d, z_vals, R, S, w['off_in'], w['off_out'], w['slot'], w['PTS'], w['RAY_IN'],
+          w['X0'], 64, w['Y8'], Y8_LD, w['H'][4], 256, w['XN'], 128, w['H5'], 384, w['FV'], 320, w['DIST_OUT'], w['RAY_OUT'])
+        n_in, n_out = w['n_in'], w['n_out']
+        # ---- inner samples: SDF value + analytic gradient
+        self.sdf.forward_with_gradient(w, n_in, cap)
+        # ---- materials
+        A = w['ACT']
+        matin = Mat(w['Y8'])
+        self.m_met.forward(matin, A['met'], Mat(w['OUTS'], O_MET), n_in, cap)
+        self.m_rough.forward(matin, A['rough'], Mat(w['OUTS'], O_ROUGH), n_in, cap)
+        self.m_alb.forward(matin, A['alb'], Mat(w['OUTS'], O_ALB), n_in, cap)
+        hp = human_poses.contiguous() if self.human else None
+        K('nero_shade_prep_fwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['E'], E_LD, w['GEO'], hp, w['EH'] if self.human else None,
+          64, 8, n_in, cap)
+        self.m_outer.forward(Mat(w['E'], E_IDER), A['odir'], Mat(w['OUTS'], O_LDIR), n_in, cap)
+        self.m_outer.forward(Mat(w['E'], E_IDEN), A['odif'], Mat(w['OUTS'], O_LD), n_in, cap)
+        self.m_inner.forward(Mat(w['E'], E_PE8X), A['inner'], Mat(w['OUTS'], O_LI), n_in, cap)
+        self.m_iw.forward(Mat(w['E'], 0), A['iw'], Mat(w['OUTS'], O_IW), n_in, cap)
+        if self.human:
+            self.m_human.forward(Mat(w['EH']), A['human'], Mat(w['OUTS'], O_HUM), n_in, cap)
+        K('nero_shade_combine_fwd', w['OUTS'], w['GEO'], self.lut, self.exp_max, 1 if self.human else 0, w['COLOR_IN'], w['OCCP'], w['REFL'],
+          n_in, cap)
+        K('nero_sdf_alpha_fwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, float(cos_anneal_ratio), w['ALPHA_IN'],
+          w['GERR'], n_in, cap)
+        # ---- outer samples: NeRF++
+        self.nerf.forward(w, n_out, cap)
+        K('nero_nerf_post_fwd', w['DENS'], 4, w['RGBRAW'], 4, w['DIST_OUT'], w['ALPHA_OUT'], w['COLOR_OUT'], n_out, cap)
+        # ---- compositing
+        rgb = torch.empty(R, 3, device=self.dev)
+        K('nero_composite_fwd', w['slot'], R, S, w['ALPHA_IN'], w['COLOR_IN'], w['ALPHA_OUT'], w['COLOR_OUT'], rgb, None)
+        # ---- occlusion loss
+        occ_on = cfg['apply_occ_loss'] and step >= cfg['occ_loss_step']
+        P = 0
+        if occ_on:
+            K('nero_occ_select', w['PTS'], w['Y8'], Y8_LD, Y8_SDF, w['G'], w['RAY_IN'], rays_d, float(cfg['occ_sdf_thresh']), n_in, cap,
+              w['SEL'], w['OCC_COUNT'])
+        if ops.DRY_RUN:
+            w['n_in'].fill_(100)
+            w['OCC_COUNT'].fill_(min(3000, cap))
+        counts = torch.cat([w['n_in'], w['OCC_COUNT']]).tolist()    # the one host sync of the forward pass
+        N_in = counts[0]
+        if occ_on:
+            P = self._occ_forward(counts[1], perm)
+        self.state = dict(R=R, S=S, N_in=N_in, P=P, rays_d=rays_d, hp=hp, car=float(cos_anneal_ratio), step=step)
+        return rgb, N_in, P
+
+    def _occ_forward(self, cnt, perm):
+        cfg, w = self.cfg, self.w
+        maxp = cfg['occ_loss_max_pn']
+        if cnt == 0:
+            return 0
+        sel = w['SEL']
+        if cnt > maxp:   # renderer.py:535-541 random subset
+            idx = perm if perm is not None else torch.randperm(cnt, device=self.dev)
+            sel = sel[:cnt][idx[:maxp].to(self.dev)].contiguous()
+            cnt = maxp
+            w['SEL_SUB'] = sel
+        P = cnt
+        var = self.p.deviation_network.variance.detach()
+        K('nero_occ_init', w['PTS'], w['REFL'], sel, None, P, 64, self.t_lin64, w['OCC_O'], w['OCC_D'], w['OCC_Z'], 64, w['SX0'], 64,
+          w['SC'], 256)
+        self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, P * 64)
+        K('nero_upsample', w['OCC_O'], w['OCC_D'], P, w['OCC_Z'], 64, w['SSDF'], 64, 64, 16, var, 3.0e38, 1, 1, w['OCC_NEWZ'], 16,
+          w['SX0'], 64, w['SC'], 256, None)
+        self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, P * 16)
+        K('nero_upsample', w['OCC_O'], w['OCC_D'], P, w['OCC_NEWZ'], 16, w['SSDF'], 16, 16, 16, var, 3.0e38, 1, 1, None, 0, None, 0, None, 0,
+          w['OCC_GT'])
+        w['OCC_LOSS'].zero_()
+        w['DOCC'].zero_()
+        K('nero_occ_loss', w['OCCP'], w['OCC_GT'], sel, None, P, w['OCC_LOSS'], w['DOCC'])
+        self.occ_sel = sel
+        return P
+
+    # ------------------------------------------------------------------ render_core backward
+    def render_core_backward(self, d_rgb, d_gerr, d_occ_scale):
+        """d_rgb [R,3]; d_gerr [N_in] or None; d_occ_scale: float tensor [] = dL/d(loss_occ) / P or None.
+        Accumulates into the .grad of every parameter."""
+        self._alloc_backward()
+        self.grads.ensure()
+        st, w, cfg = self.state, self.w, self.cfg
+        R, S, cap = st['R'], st['S'], st['R'] * st['S']
+        rays_d = st['rays_d']
+        n_in, n_out = w['n_in'], w['n_out']
+        var_p = self.p.deviation_network.variance
+        var = var_p.detach()
+        ws = self.ws
+        K('nero_composite_bwd', w['slot'], R, S, w['ALPHA_IN'], w['COLOR_IN'], w['ALPHA_OUT'], w['COLOR_OUT'], d_rgb.contiguous(),
+          w['dALPHA_IN'], w['dCOLOR_IN'], w['dALPHA_OUT'], w['dCOLOR_OUT'])
+        # ---- outer NeRF
+        K('nero_nerf_post_bwd', w['DENS'], 4, w['RGBRAW'], 4, w['DIST_OUT'], w['dALPHA_OUT'], w['dCOLOR_OUT'], w['dDENS'], 4, w['dRGBRAW'], 4,
+          n_out, cap)
+        self.nerf.backward(ws, w, n_out, cap)
+        # ---- shading
+        docc = None
+        if d_occ_scale is not None and st['P'] > 0:
+            docc = w['DOCC'] * d_occ_scale          # sign * dL/dloss_occ / P   (tiny elementwise op on [cap])
+        K('nero_shade_combine_bwd', w['OUTS'], w['GEO'], self.lut, self.exp_max, 1 if self.human else 0, w['dCOLOR_IN'], docc, w['DOUTS'],
+          w['DNOV'], n_in, cap)
+        A = w['ACT']
+        dHa, dHb = w['dHa'], w['dHb']
+        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LDIR), Mat(w['E'], E_IDER), A['odir'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dir']), dx_ncol=72)
+        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LD), Mat(w['E'], E_IDEN), A['odif'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dif']), dx_ncol=72)
+        self.m_inner.backward(ws, Mat(w['DOUTS'], O_LI), Mat(w['E'], E_PE8X), A['inner'], dHa, dHb, n_in, cap, dX=Mat(w['dE_inn']), dx_ncol=72)
+        self.m_iw.backward(ws, Mat(w['DOUTS'], O_IW), Mat(w['E'], 0), A['iw'], dHa, dHb, n_in, cap)
+        if self.human:
+            self.m_human.backward(ws, Mat(w['DOUTS'], O_HUM), Mat(w['EH']), A['human'], dHa, dHb, n_in, cap, dX=Mat(w['dEH']), dx_ncol=24)
+        K('nero_shade_prep_bwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['GEO'], w['dE_dir'], 128, w['dE_inn'], 128, w['dE_dif'], 128,
+          w['dEH'] if self.human else None, 64, st['hp'], w['DNOV'], w['DOUTS'], w['DG'], n_in, cap)
+        matin = Mat(w['Y8'])
+        self.m_rough.backward(ws, Mat(w['DOUTS'], O_ROUGH), matin, A['rough'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256)
+        self.m_met.backward(ws, Mat(w['DOUTS'], O_MET), matin, A['met'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']))
+        self.m_alb.backward(ws, Mat(w['DOUTS'], O_ALB), matin, A['alb'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']))
+        # ---- SDF -> alpha
+        w['D_INV_S'].zero_()
+        dg = None if d_gerr is None else d_gerr.contiguous()
+        K('nero_sdf_alpha_bwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, st['car'], w['dALPHA_IN'], dg,
+          w['dY8'], Y8_LD, w['DG'], w['D_INV_S'], n_in, cap)
+        frozen = cfg['freeze_inv_s_step'] is not None and st['step'] < cfg['freeze_inv_s_step']
+        if not frozen:
+            inv_s = torch.exp(var * 10.0)
+            inr = ((inv_s >= 1e-6) & (inv_s <= 1e6)).float()
+            var_p.grad.add_((w['D_INV_S'][0] * 10.0 * inv_s * inr).reshape(var_p.shape))
+        # ---- SDF network (value + gradient paths)
+        self.sdf.backward(ws, w, n_in, cap, None)

@@ -26,6 +26,7 @@ lib = ctypes.CDLL(_LIB_PATH)
 
 launch_count = 0  # kernels launched through the C ABI (bench.py reports it)
 DEBUG_GEMM = os.environ.get('NERO_DEBUG_GEMM', '')
+DRY_RUN = bool(os.environ.get('NERO_DRY_RUN'))   # tests only: walk the host logic on CPU tensors without launching
 
 
 def _ptr(t):
@@ -35,6 +36,8 @@ def _ptr(t):
 
 
 def _stream():
+    if DRY_RUN:
+        return ctypes.c_void_p(0)
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -84,20 +87,22 @@ class PreparedLayer:
         else:
             self.img_t = None
         self.w_eff = torch.zeros(N, K, dtype=torch.float32, device=device)
-        self.bias_pad = torch.zeros(self.n_pad, dtype=torch.float32, device=device)
 
     def prep(self):
         global launch_count
         w = self.weight.detach()
         g = None if self.g is None else self.g.detach()
+        if DRY_RUN:
+            return
         rc = lib.nero_prep_weight(_ptr(w), _ptr(g), self.K, self.row0, self.nrows, _ptr(self.kmap), ctypes.c_float(1.0),
                                   _ptr(self.img_f), self.n_pad, _ptr(self.img_t), self.t_npad if self.img_t is not None else 0,
                                   self.t_cols[0] if self.t_cols else 0, self.t_cols[1] if self.t_cols else 0,
                                   _ptr(self.w_eff), self.K, _stream())
         _check(rc, 'nero_prep_weight')
         launch_count += 1
-        if self.bias is not None:
-            self.bias_pad[:self.nrows].copy_(self.bias.detach()[self.row0:self.row0 + self.nrows])
+
+    def bias_view(self):
+        return None if self.bias is None else self.bias.detach()[self.row0:self.row0 + self.nrows]
 
     # fp32 layout-space weights for the debug emulation
     def w_layout(self):
@@ -171,13 +176,18 @@ def linear(A: Mat, layer: PreparedLayer, out: Mat, ncol_out, *, transposed=False
         bias = None
     else:
         img, n_pad, k_chunks, k_valid = layer.img_f, layer.n_pad, layer.k_chunks, layer.k_valid
-        bias = layer.bias_pad if (use_bias and layer.bias is not None) else None
+        bias = layer.bias_view() if use_bias else None
     if m_cap is None:
         m_cap = A.t.shape[0]
     if DEBUG_GEMM == 'torch':
         return _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, oscale, H, hscale, dact, V, out2,
                              addend, ncol_main, tail, m_ptr, m_cap, bias, k_valid)
-    rc = lib.nero_linear(A.ptr(), A.ld, k_valid, _ptr(img), n_pad, k_chunks, _ptr(bias), out.ptr(), out.ld, ncol_out,
+    if DRY_RUN:
+        assert A.ld % 4 == 0 and A.c0 % 4 == 0 and ncol_out <= n_pad and img is not None
+        assert A.c0 + k_valid <= A.t.shape[1] and out.c0 + ncol_out <= out.t.shape[1], (A.c0, k_valid, A.t.shape, out.c0, ncol_out, out.t.shape)
+        assert mode != EPI_TANGENT or (H is not None and V is not None and out2 is not None)
+        return
+    rc = lib.nero_linear(A.ptr(), A.ld, k_valid, _ptr(img), n_pad, k_chunks, _ptr(bias), 0 if bias is None else bias.numel(), out.ptr(), out.ld, ncol_out,
                          ctypes.c_float(oscale), mode, act, ctypes.c_float(act_param),
                          H.ptr() if H else None, H.ld if H else 0, ctypes.c_float(hscale), dact,
                          V.ptr() if V else None, V.ld if V else 0, out2.ptr() if out2 else None, out2.ld if out2 else 0,
@@ -246,13 +256,17 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
         ws.bias_partial[0, :n_valid] = dY.t[:M, dY.c0:dY.c0 + n_valid].sum(0)
     else:
         P = ws.P
-        rc = lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
+        rc = 0 if DRY_RUN else lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
                             dY2.ptr() if dY2 else None, dY2.ld if dY2 else 0, X2.ptr() if X2 else None, X2.ld if X2 else 0,
                             _ptr(ws.partial), ws.ld, ws.rows, _ptr(ws.bias_partial), n_rows_pad, k_pad, P, _ptr(m_ptr),
                             m_cap, _stream())
         _check(rc, 'nero_wgrad')
         launch_count += ceil_div(n_rows_pad, 128) * max(1, ceil_div(k_pad, 256))
     g = None if layer.g is None else layer.g.detach()
+    if DRY_RUN:
+        assert grad_w is not None and (grad_b is not None or not with_bias) and (g is None or grad_g is not None)
+        assert dY.c0 + n_valid <= dY.t.shape[1] and X.c0 + k_valid <= X.t.shape[1], (dY.c0, n_valid, dY.t.shape, X.c0, k_valid, X.t.shape)
+        return
     rc = lib.nero_wgrad_finish(_ptr(ws.partial), ws.P, ws.rows, ws.ld, _ptr(ws.bias_partial) if with_bias else None,
                                layer.K, layer.row0, layer.nrows, _ptr(layer.kmap), ctypes.c_float(1.0),
                                _ptr(layer.weight.detach()), _ptr(g), _ptr(grad_w), _ptr(grad_g),
@@ -265,7 +279,33 @@ def colsum(X: Mat, ncol, out, w: Mat = None, m_ptr=None, m_cap=None):
     global launch_count
     if m_cap is None:
         m_cap = X.t.shape[0]
+    if DRY_RUN:
+        return
     rc = lib.nero_colsum(X.ptr(), X.ld, ncol, w.ptr() if w else None, w.ld if w else 0, _ptr(m_ptr), m_cap, _ptr(out),
                          _stream())
     _check(rc, 'nero_colsum')
+    launch_count += 1
+
+
+def K(name, *args):
+    """Generic launcher: tensors / Mat -> device pointers, float -> c_float, int stays int, None -> NULL; the
+    current CUDA stream is appended as the last argument."""
+    global launch_count
+    conv = []
+    for a in args:
+        if a is None:
+            conv.append(ctypes.c_void_p(0))
+        elif isinstance(a, torch.Tensor):
+            conv.append(ctypes.c_void_p(a.data_ptr()))
+        elif isinstance(a, Mat):
+            conv.append(a.ptr())
+        elif isinstance(a, float):
+            conv.append(ctypes.c_float(a))
+        else:
+            conv.append(int(a))
+    if DRY_RUN:
+        getattr(lib, name)
+        return
+    rc = getattr(lib, name)(*conv, _stream())
+    _check(rc, name)
     launch_count += 1

@@ -1,0 +1,233 @@
+"""Drop-in replacements for the reference's renderers (network/renderer.py): same registry name, constructor,
+cfg keys, forward(data) contract, output dictionaries and state_dict layout -- backed by the sm_100a kernels of
+libnero_b200 instead of PyTorch ops.
+
+    from nero_b200.renderer import name2renderer      # {'shape': NeROShapeRenderer, ...}
+    net = name2renderer[cfg['network']](cfg).cuda()    # exactly what train/trainer.py:52 does
+    outputs = net({'step': step})                      # train/trainer.py:128
+
+Reference: network/renderer.py:63-647 (NeROShapeRenderer), :917-920 (name2renderer).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .params import SDFParams, VarianceParams, NeRFParams, ShadingParams
+
+
+class _RenderCoreFn(torch.autograd.Function):
+    """render_core as ONE autograd node: forward and backward are kernel sequences (engine.py); parameter gradients
+    are accumulated straight into the flat .grad buffer (they are not returned through autograd)."""
+
+    @staticmethod
+    def forward(ctx, engine, rays_o, rays_d, z_vals, human_poses, car, step, perm, *params):
+        rgb, n_in, P = engine.render_core_forward(rays_o, rays_d, z_vals, human_poses, car, step, perm)
+        w = engine.w
+        gerr = w['GERR'][:n_in].clone() if n_in > 0 else torch.zeros(1, device=rgb.device)
+        loss_occ = (w['OCC_LOSS'][0] / P).clone() if P > 0 else torch.zeros(1, device=rgb.device)
+        ctx.engine, ctx.P, ctx.n_in, ctx.nparams = engine, P, n_in, len(params)
+        return rgb, gerr, loss_occ
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_gerr, d_occ):
+        e = ctx.engine
+        dscale = (d_occ.reshape(()) / ctx.P) if ctx.P > 0 else None
+        e.render_core_backward(d_rgb, d_gerr if ctx.n_in > 0 else None, dscale)
+        return (None,) * (8 + ctx.nparams)
+
+
+class NeROShapeRenderer(nn.Module):
+    default_cfg = {
+        'std_net': 'default', 'std_act': 'exp', 'inv_s_init': 0.3, 'freeze_inv_s_step': None,
+        'sdf_net': 'default', 'sdf_activation': 'none', 'sdf_bias': 0.5, 'sdf_n_layers': 8, 'sdf_freq': 6, 'sdf_d_out': 257,
+        'geometry_init': True,
+        'shader_config': {},
+        'n_samples': 64, 'n_bg_samples': 32, 'inf_far': 1000.0, 'n_importance': 64, 'up_sample_steps': 4, 'perturb': 1.0,
+        'anneal_end': 50000, 'train_ray_num': 512, 'test_ray_num': 1024, 'clip_sample_variance': True,
+        'database_name': 'nerf_synthetic/lego/black_800',
+        'test_downsample_ratio': True, 'downsample_ratio': 0.25, 'val_geometry': False,
+        'rgb_loss': 'charbonier', 'apply_occ_loss': True, 'occ_loss_step': 20000, 'occ_loss_max_pn': 2048, 'occ_sdf_thresh': 0.01,
+        'fixed_camera': False,
+    }
+
+    def __init__(self, cfg, training=True):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        c = self.cfg
+        if c['std_act'] != 'exp' or c['sdf_activation'] != 'none':
+            raise NotImplementedError('only std_act=exp / sdf_activation=none (the values every shipped YAML uses)')
+        self.sdf_network = SDFParams(d_out=c['sdf_d_out'], d_in=3, d_hidden=256, n_layers=c['sdf_n_layers'],
+                                     skip_in=(c['sdf_n_layers'] // 2,), multires=c['sdf_freq'], bias=c['sdf_bias'],
+                                     geometric_init=c['geometry_init'])
+        self.deviation_network = VarianceParams(c['inv_s_init'])
+        self.outer_nerf = NeRFParams()
+        with torch.no_grad():
+            self.outer_nerf.rgb_linear.bias.fill_(float(np.log(0.5)))
+        self.color_network = ShadingParams(c['shader_config'])
+        self._engine = None
+        self._weights_dirty = True
+        if training:
+            self._init_dataset()
+
+    # ------------------------------------------------------------------ engine plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine import ShapeEngine
+            from . import ops as _ops
+            if self.deviation_network.variance.device.type != 'cuda' and not _ops.DRY_RUN:
+                raise RuntimeError('NeROShapeRenderer must be moved to a CUDA device (.cuda()) -- there is no CPU path')
+            self._engine = ShapeEngine(self, self.cfg)
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None      # parameters are re-created on .cuda()/.to(): rebuild the prepared layers lazily
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ helpers kept from the reference contract
+    def get_anneal_val(self, step):
+        return 1.0 if self.cfg['anneal_end'] < 0 else float(np.min([1.0, step / self.cfg['anneal_end']]))
+
+    @staticmethod
+    def near_far_from_sphere(rays_o, rays_d):
+        a = torch.sum(rays_d ** 2, dim=-1, keepdim=True)
+        b = 2.0 * torch.sum(rays_o * rays_d, dim=-1, keepdim=True)
+        mid = 0.5 * (-b) / a
+        return torch.clamp(mid - 1.0, min=1e-3), mid + 1.0
+
+    def get_human_coordinate_poses(self, poses):
+        pn = poses.shape[0]
+        cam_cen = (-poses[:, :, :3].permute(0, 2, 1) @ poses[:, :, 3:])[..., 0]
+        if not self.cfg['fixed_camera']:
+            cam_cen = torch.cat([cam_cen[:, :2], torch.zeros_like(cam_cen[:, :1])], -1)
+        Y = torch.zeros([pn, 3], device=poses.device, dtype=poses.dtype)
+        Y[:, 2] = -1.0
+        Z = poses[:, 2, :3].clone()
+        Z[:, 2] = 0
+        Z = F.normalize(Z, dim=-1)
+        X = torch.cross(Y, Z, dim=-1)
+        R = torch.stack([X, Y, Z], 1)
+        t = -R @ cam_cen[:, :, None]
+        return torch.cat([R, t], -1)
+
+    def compute_rgb_loss(self, rgb_pr, rgb_gt):
+        kind = self.cfg['rgb_loss']
+        if kind == 'l2':
+            return torch.sum((rgb_pr - rgb_gt) ** 2, -1)
+        if kind == 'l1':
+            return torch.sum(F.l1_loss(rgb_pr, rgb_gt, reduction='none'), -1)
+        if kind == 'smooth_l1':
+            return torch.sum(F.smooth_l1_loss(rgb_pr, rgb_gt, reduction='none', beta=0.25), -1)
+        if kind == 'charbonier':
+            return torch.sqrt(torch.sum((rgb_gt - rgb_pr) ** 2, dim=-1) + 0.001)
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ the hot path
+    def sample_ray(self, rays_o, rays_d, near, far, perturb, rand_inner=None, rand_bg=None):
+        """z_vals [R, n_samples+n_importance+n_bg_samples] (network/renderer.py:403-443).  Random draws are made with
+        torch in the reference's order (renderer.py:416, :422) unless passed in."""
+        e = self.engine
+        e.prepare_weights()
+        R = rays_o.shape[0]
+        if perturb > 0 and rand_inner is None:
+            rand_inner = torch.rand([R, 1], device=rays_o.device)
+            rand_bg = torch.rand([R, self.cfg['n_bg_samples']], device=rays_o.device)
+        if perturb <= 0:
+            rand_inner = rand_bg = None
+        with torch.no_grad():
+            return e.sample_ray(rays_o.contiguous(), rays_d.contiguous(), near.contiguous(), far.contiguous(),
+                                None if rand_inner is None else rand_inner.contiguous(),
+                                None if rand_bg is None else rand_bg.contiguous())
+
+    def render_core(self, rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio=0.0, step=None, is_train=True, perm=None):
+        if not is_train:
+            raise NotImplementedError('validation render (compute_validation_info) is not part of the B200 hot path yet')
+        e = self.engine
+        if step < 1000:
+            raise NotImplementedError('init_sdf_reg outputs (step < 1000) are not implemented in the B200 path yet')
+        params = [p for p in self.parameters()]
+        rgb, gerr, loss_occ = _RenderCoreFn.apply(e, rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(),
+                                                  human_poses.contiguous(), float(cos_anneal_ratio), int(step), perm, *params)
+        outputs = {'ray_rgb': rgb, 'gradient_error': gerr}
+        inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)
+        if self.cfg['freeze_inv_s_step'] is not None and step < self.cfg['freeze_inv_s_step']:
+            inv_s = inv_s.detach()
+        outputs['std'] = torch.mean(1 / inv_s) if e.state['N_in'] > 0 else torch.zeros(1, device=rgb.device)
+        if self.cfg['apply_occ_loss']:
+            outputs['loss_occ'] = loss_occ
+        return outputs
+
+    def render(self, rays_o, rays_d, near, far, human_poses, perturb_overwrite=-1, cos_anneal_ratio=0.0, is_train=True, step=None):
+        perturb = self.cfg['perturb']
+        if perturb_overwrite >= 0:
+            perturb = perturb_overwrite
+        z_vals = self.sample_ray(rays_o, rays_d, near, far, perturb)
+        return self.render_core(rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train)
+
+    # ------------------------------------------------------------------ dataset plumbing (host side, unchanged semantics)
+    def _init_dataset(self):
+        """network/renderer.py:136-165 -- needs the reference's `dataset` package on sys.path (drop-in scenario)."""
+        from dataset.database import parse_database_name, get_database_split   # noqa: provided by the host repo
+        from utils.base_utils import color_map_forward
+        self.database = parse_database_name(self.cfg['database_name'])
+        self.train_ids, self.test_ids = get_database_split(self.database)
+        self.train_ids = np.asarray(self.train_ids)
+
+        def info(ids):
+            imgs = color_map_forward(np.stack([self.database.get_image(i) for i in ids], 0)).astype(np.float32)
+            Ks = np.stack([self.database.get_K(i) for i in ids], 0).astype(np.float32)
+            poses = np.stack([self.database.get_pose(i) for i in ids], 0).astype(np.float32)
+            return {'imgs': torch.from_numpy(imgs).permute(0, 3, 1, 2), 'Ks': torch.from_numpy(Ks), 'poses': torch.from_numpy(poses)}
+        self.train_imgs_info, self.test_imgs_info = info(self.train_ids), info(self.test_ids)
+        self.train_num, self.test_num = len(self.train_ids), len(self.test_ids)
+        self.train_batch, self.train_poses, self.tbn, _, _ = self._construct_ray_batch(self.train_imgs_info)
+        self.train_poses = self.train_poses.float()
+        self._shuffle_train_batch()
+
+    def _shuffle_train_batch(self):
+        self.train_batch_i = 0
+        idx = torch.randperm(self.tbn, device='cpu')
+        for k, v in self.train_batch.items():
+            self.train_batch[k] = v[idx].pin_memory() if torch.cuda.is_available() else v[idx]
+
+    def _construct_ray_batch(self, imgs_info, device='cpu'):
+        imn, _, h, w = imgs_info['imgs'].shape
+        ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
+        coords = torch.stack([xs, ys], -1).float()[None].repeat(imn, 1, 1, 1).reshape(imn, h * w, 2)
+        coords = torch.cat([coords + 0.5, torch.ones(imn, h * w, 1)], 2)
+        dirs = coords @ torch.inverse(imgs_info['Ks']).permute(0, 2, 1)
+        imgs = imgs_info['imgs'].permute(0, 2, 3, 1).reshape(imn, h * w, 3)
+        idxs = torch.arange(imn, dtype=torch.int64)[:, None, None].repeat(1, h * w, 1)
+        rn = imn * h * w
+        batch = {'dirs': dirs.float().reshape(rn, 3), 'rgbs': imgs.float().reshape(rn, 3), 'idxs': idxs.reshape(rn, 1)}
+        return batch, imgs_info['poses'], rn, h, w
+
+    def _process_ray_batch(self, ray_batch, poses):
+        rays_d = ray_batch['dirs']
+        idxs = ray_batch['idxs'][..., 0]
+        rays_o = (poses[:, :, :3].permute(0, 2, 1) @ -poses[:, :, 3:])[idxs, :, 0]
+        rays_d = (poses[idxs, :, :3].permute(0, 2, 1) @ rays_d.unsqueeze(-1))[..., 0]
+        rays_d = F.normalize(rays_d, dim=-1)
+        near, far = self.near_far_from_sphere(rays_o, rays_d)
+        return rays_o, rays_d, near, far, self.get_human_coordinate_poses(poses)[idxs]
+
+    def train_step(self, step):
+        rn = self.cfg['train_ray_num']
+        dev = self.deviation_network.variance.device
+        batch = {k: v[self.train_batch_i:self.train_batch_i + rn].to(dev, non_blocking=True) for k, v in self.train_batch.items()}
+        self.train_batch_i += rn
+        if self.train_batch_i + rn >= self.tbn:
+            self._shuffle_train_batch()
+        rays_o, rays_d, near, far, hp = self._process_ray_batch(batch, self.train_poses.to(dev))
+        outputs = self.render(rays_o, rays_d, near, far, hp, -1, self.get_anneal_val(step), is_train=True, step=step)
+        outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], batch['rgbs'])
+        return outputs
+
+    def forward(self, data):
+        if 'eval' in data:
+            raise NotImplementedError('validation render is outside the B200 hot path (SURVEY.md section 8f item 3)')
+        return self.train_step(data['step'])
+
+
+name2renderer = {'shape': NeROShapeRenderer}
