@@ -369,7 +369,7 @@ class ShapeEngine:
         w = {}
         ns = self.cfg['n_samples']
         caps = max(R * ns, self.cfg['occ_loss_max_pn'] * 64)
-        w.update(SX0=z(caps, 64), SA=z(caps, 256), SB=z(caps, 256), SC=z(caps, 256), SSDF=z(caps, 1),
+        w.update(SX0=z(caps, 64), SA=z(caps, 256), SB=z(caps, 256), SC=z(caps, 256), SSDF=z(caps, 1), SSDF0=z(R * ns, 1),
                  ZA=z(R, 128), ZB=z(R, 128), SDFA=z(R, 128), SDFB=z(R, 128), NEWZ=z(R, 32))
         w.update(cnt_in=z(R, dt=torch.int32), cnt_out=z(R, dt=torch.int32), off_in=z(R, dt=torch.int32), off_out=z(R, dt=torch.int32),
                  n_in=z(1, dt=torch.int32), n_out=z(1, dt=torch.int32), slot=z(R, S, dt=torch.int32))
@@ -423,8 +423,8 @@ class ShapeEngine:
         var = self.p.deviation_network.variance.detach()
         K('nero_sample_init', rays_o, rays_d, near, far, R, n, nb, self.t_lin, self.t_bg, self.t_bg_lo, self.t_bg_hi,
           rand_inner, rand_bg, w['ZA'], 128, Mat(z_vals, n + nimp), S, w['SX0'], 64, w['SC'], 256)
-        self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, R * n)
-        cur_z, cur_sdf, lds = w['ZA'], w['SSDF'], n
+        self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF0'], None, R * n)   # coarse sdf kept apart:
+        cur_z, cur_sdf, lds = w['ZA'], w['SSDF0'], n                                        # SSDF is reused per iteration
         nxt_z, nxt_sdf = w['ZB'], w['SDFB']
         cur_n = n
         for i in range(steps):
