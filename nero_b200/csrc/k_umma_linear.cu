@@ -1,14 +1,19 @@
 // tcgen05 (UMMA) linear-layer kernel: OUT[M, N] = epilogue( A[M, K] * W[N, K]^T ).
 //
-//  * A is fp32 row-major in HBM.  Producer warps load it (coalesced float4), split every value into
-//    bf16 hi + bf16 lo (error-compensated "split-bf16": x ~= hi + lo, ~2^-17 relative) and store both planes
-//    into the K-major SWIZZLE_128B shared-memory operand layout the tensor core reads.
+//  * A is fp32 row-major in HBM.  EIGHT producer warps (two groups alternating K-chunks, so one group's global
+//    loads are in flight while the other converts) load it with coalesced float4, split every value into
+//    bf16 hi + bf16 lo (error-compensated "split-bf16": x ~= hi + lo, ~2^-17 relative; packed cvt.rn.bf16x2) and
+//    store both planes into the K-major SWIZZLE_128B shared-memory operand layout the tensor core reads.
 //  * W is pre-split and pre-swizzled once per step by nero_prep_weight (k_weights.cu) into the exact
 //    shared-memory image, so a K-chunk of it is ONE cp.async.bulk (UBLKCP) from L2, completing on an mbarrier.
 //  * One elected thread issues tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32 in TMEM), three MMAs per k-step:
-//    A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (the lo*lo term, ~2^-18 relative, is dropped).
-//  * The fp32 accumulator tile (128 x N) lives in TMEM, double buffered (2 x 256 columns), so the epilogue
-//    warps (tcgen05.ld -> bias/activation/derivative products -> HBM) overlap the next tile's MMAs.
+//    A_lo*W_hi + A_hi*W_lo + A_hi*W_hi  (the lo*lo term, ~2^-18 relative, is dropped).
+//  * The fp32 accumulator tile (128 x N) lives in TMEM, double buffered (2 x 256 columns), so the EIGHT epilogue
+//    warps (tcgen05.ld -> bias/activation/derivative products -> HBM) overlap the next tile's MMAs.  Every global
+//    access of the epilogue is staged through a per-warp shared-memory transpose buffer so that warps read and
+//    write 64-byte row segments (8 rows per instruction) instead of one row per lane.
+//  * Epilogue math is specialised at compile time (template EPI) and uses ex2/lg2 approximations for
+//    softplus(beta=100) and its derivative (absolute error ~1e-9 on activations of O(1)).
 //  * Persistent CTAs (one per SM), tiles of 128 rows, row count read from device memory (no host sync for the
 //    data-dependent number of live samples).
 //
@@ -34,28 +39,125 @@ struct LinearParams {
   const int* m_ptr; int m_cap;
 };
 
+// compile-time epilogue kinds
+enum EpiKind : int { EK_BIAS_SOFTPLUS = 0, EK_BIAS_RELU = 1, EK_BIAS_GENERIC = 2, EK_DACT_SOFTPLUS = 3, EK_DACT_RELU = 4,
+                     EK_DACT_NONE = 5, EK_TANGENT = 6 };
+
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 4, kProdWarps = 4;
-constexpr int kLinearThreads = (kEpiWarps + kProdWarps + 2) * 32;  // + MMA warp + W-loader warp
-constexpr uint32_t kABytes = BM * 128;                             // one bf16 plane of an A stage (16 KB)
+constexpr int kEpiWarps = 8, kProdWarps = 8;
+constexpr int kMmaWarp = kEpiWarps + kProdWarps, kLoadWarp = kMmaWarp + 1;
+constexpr int kLinearThreads = (kEpiWarps + kProdWarps + 2) * 32;
+constexpr uint32_t kABytes = BM * 128;           // one bf16 plane of an A stage (16 KB)
+constexpr int kStagePitch = 20;                  // floats per row of the per-warp transpose buffer (16 cols + pad)
+constexpr uint32_t kStageWarpBytes = 32 * kStagePitch * 4;
 
 template <int NPAD> struct LinCfg {
-  static constexpr uint32_t b_plane = NPAD * 128;                  // one bf16 plane of a W stage
+  static constexpr uint32_t b_plane = NPAD * 128;
   static constexpr uint32_t stage_bytes = 2 * kABytes + 2 * b_plane;
   static constexpr int stages = (stage_bytes * 4 <= 200 * 1024) ? 4 : (stage_bytes * 3 <= 200 * 1024) ? 3 : 2;
-  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 1024 /*bias*/ + 256 /*barriers*/;
+  static constexpr uint32_t epi_bytes = kEpiWarps * kStageWarpBytes;   // 20 KB
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + epi_bytes + 1024 /*align*/ + 1024 /*bias*/ + 256 /*barriers*/;
 };
 
-template <int NPAD>
+// fast softplus(beta=100): max error ~1e-9 absolute (ex2/lg2 approximations, 1+t rounding)
+__device__ __forceinline__ float softplus100_fast(float a) {
+  const float z = 100.0f * a;
+  const float t = exp2f(fminf(z, 20.0f) * 1.4426950408889634f);      // MUFU.EX2
+  const float h = __log2f(1.0f + t) * (0.6931471805599453f * 0.01f);  // MUFU.LG2
+  return z > 20.0f ? a : h;
+}
+__device__ __forceinline__ float dsoftplus100_from_h_fast(float h) {
+  const float z = 100.0f * h;
+  return z > 20.0f ? 1.0f : 1.0f - exp2f(-z * 1.4426950408889634f);
+}
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+  const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  hi = hb;
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// 16 columns of one TMEM lane group
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// coalesced load of a [32 rows x 16 cols] block (row-major global, leading dim ld) into registers of the
+// "lane = row" layout, through the warp's transpose buffer.  Rows >= rows_valid / cols >= cols_valid read as 0.
+__device__ __forceinline__ void load_block16(const float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec,
+                                             float* stage, int lane, float* r) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid) {
+      const float* p = g + size_t(row) * ld + q;
+      if (vec && q + 3 < cols_valid) x = *reinterpret_cast<const float4*>(p);
+      else {
+        if (q < cols_valid) x.x = p[0];
+        if (q + 1 < cols_valid) x.y = p[1];
+        if (q + 2 < cols_valid) x.z = p[2];
+        if (q + 3 < cols_valid) x.w = p[3];
+      }
+    }
+    *reinterpret_cast<float4*>(stage + row * kStagePitch + q) = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 x = *reinterpret_cast<const float4*>(stage + lane * kStagePitch + j * 4);
+    r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
+  }
+  __syncwarp();
+}
+// the reverse: registers ("lane = row") -> coalesced global store of columns [0, cols_valid)
+__device__ __forceinline__ void store_block16(float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec,
+                                              float* stage, int lane, const float* r) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4*>(stage + lane * kStagePitch + j * 4) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+    if (row < rows_valid && q < cols_valid) {
+      const float4 x = *reinterpret_cast<const float4*>(stage + row * kStagePitch + q);
+      float* p = g + size_t(row) * ld + q;
+      if (vec && q + 3 < cols_valid) *reinterpret_cast<float4*>(p) = x;
+      else {
+        p[0] = x.x;
+        if (q + 1 < cols_valid) p[1] = x.y;
+        if (q + 2 < cols_valid) p[2] = x.z;
+        if (q + 3 < cols_valid) p[3] = x.w;
+      }
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ bool vec_ok(const float* p, int ld) {
+  return ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+template <int NPAD, int EPI>
 __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const LinearParams p) {
   using Cfg = LinCfg<NPAD>;
   constexpr int STAGES = Cfg::stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes + 1024);
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * Cfg::stage_bytes);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::stage_bytes + Cfg::epi_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes + Cfg::epi_bytes + 1024);
   uint64_t* full = bars;                    // [STAGES]
   uint64_t* empty = bars + STAGES;          // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;      // [2]
@@ -68,86 +170,96 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
   const int num_tiles = (M + BM - 1) / BM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kProdWarps + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kProdWarps / 2 + 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == kEpiWarps + kProdWarps + 1) tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_bias) ? p.bias[i] : 0.0f;
+  if (warp == kLoadWarp) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_bias) ? p.bias[i] : 0.0f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kEpiWarps) {
-    // ============================== epilogue warps: TMEM -> registers -> HBM
+    // ============================== epilogue warps: TMEM -> registers -> (smem transpose) -> HBM
+    const int lg = warp & 3;            // TMEM lane group (rows lg*32 .. +31 of the tile)
+    const int half = warp >> 2;         // which 16-column blocks (interleaved) this warp handles
+    float* stg = s_epi + warp * (32 * kStagePitch);
+    constexpr int NBLK = NPAD / 16;
+    constexpr bool kBias = (EPI == EK_BIAS_SOFTPLUS || EPI == EK_BIAS_RELU || EPI == EK_BIAS_GENERIC);
+    const int nmain = kBias ? p.ncol_out : min(p.ncol_out, p.ncol_main);
+    const bool v_out = vec_ok(p.out, p.ldo);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tcgen05_fence_after();
-      const int row = tile * BM + warp * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * 256);
+      const int row0 = tile * BM + lg * 32;
+      const int rows_valid = min(32, M - row0);       // may be <= 0
+      const uint32_t taddr = tmem_base + (uint32_t(lg * 32) << 16) + uint32_t(acc * 256);
 #pragma unroll 1
-      for (int cc = 0; cc < (NPAD + 31) / 32; ++cc) {
-        float v[32];
-        tmem_ld32(taddr + cc * 32, v);
+      for (int b = half; b < NBLK; b += 2) {
+        const int c0 = b * 16;
+        if (c0 >= p.ncol_out) break;
+        float v[16];
+        tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
-        const int c0 = cc * 32;
-        if (row_ok && c0 < p.ncol_out) {
-          float o1[32];
-          float o2[32];
-          const float* hrow = p.H ? p.H + size_t(row) * p.ldh + c0 : nullptr;
-          const float* vrow = p.V ? p.V + size_t(row) * p.ldv + c0 : nullptr;
-          const float* arow = p.addend ? p.addend + size_t(row) * p.ldadd + c0 : nullptr;
+        if (rows_valid <= 0) continue;
+        float r[16];
+        if constexpr (kBias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j;
-            const float a = v[j];
-            float r = 0.0f, r2 = 0.0f;
-            if (col < p.ncol_out) {
-              if (p.mode == EPI_BIAS_ACT) {
-                r = p.oscale * apply_act(a + s_bias[col], p.act, p.act_param);
-              } else if (col < p.ncol_main) {
-                const float s = hrow ? dact_from_h(hrow[j] * p.hscale, p.dact) : 1.0f;
-                r = p.oscale * s * a;
-                if (arow) r += arow[j];
-                if (p.mode == EPI_TANGENT) r2 = 100.0f * (1.0f - s) * vrow[j] * a;
-              } else {
-                r = p.oscale * a;  // tail columns (skip-connection branch)
-              }
-            }
-            o1[j] = r; o2[j] = r2;
+          for (int j = 0; j < 16; ++j) {
+            const float x = v[j] + s_bias[c0 + j];
+            float y;
+            if constexpr (EPI == EK_BIAS_SOFTPLUS) y = softplus100_fast(x);
+            else if constexpr (EPI == EK_BIAS_RELU) y = fmaxf(x, 0.0f);
+            else y = apply_act(x, p.act, p.act_param);
+            r[j] = p.oscale * y;
           }
-          // ---- stores
-          const int nmain = (p.mode == EPI_BIAS_ACT) ? p.ncol_out : min(p.ncol_out, p.ncol_main);
-          float* orow = p.out + size_t(row) * p.ldo + c0;
-          const bool vec_ok = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (c0 + 32 <= nmain);
-          if (vec_ok) {
+          store_block16(p.out + size_t(row0) * p.ldo + c0, p.ldo, rows_valid, nmain - c0, v_out, stg, lane, r);
+        } else {
+          const int cm = nmain - c0;   // main columns in this block (may be <= 0)
+          float s[16];
+          if constexpr (EPI == EK_DACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(o1[j], o1[j + 1], o1[j + 2], o1[j + 3]);
+            for (int j = 0; j < 16; ++j) s[j] = 1.0f;
           } else {
+            load_block16(p.H + size_t(row0) * p.ldh + c0, p.ldh, rows_valid, cm, vec_ok(p.H, p.ldh), stg, lane, s);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (c0 + j < nmain) orow[j] = o1[j];
-          }
-          if (p.mode == EPI_TANGENT) {
-            float* o2row = p.out2 + size_t(row) * p.ldo2 + c0;
-            const bool vec2 = ((p.ldo2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out2) & 15) == 0) && (c0 + 32 <= nmain);
-            if (vec2) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o2row + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (c0 + j < nmain) o2row[j] = o2[j];
+            for (int j = 0; j < 16; ++j) {
+              if constexpr (EPI == EK_DACT_RELU) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
+              else s[j] = dsoftplus100_from_h_fast(s[j] * p.hscale);
             }
           }
-          if (p.mode != EPI_BIAS_ACT && p.tail && c0 + 32 > p.ncol_main) {
-            float* trow = p.tail + size_t(row) * p.ldt;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = c0 + j;
-              if (col >= p.ncol_main && col < p.ncol_out) trow[col - p.ncol_main] = o1[j];
+          for (int j = 0; j < 16; ++j) r[j] = p.oscale * s[j] * v[j];
+          if (p.addend) {
+            float a[16];
+            load_block16(p.addend + size_t(row0) * p.ldadd + c0, p.ldadd, rows_valid, cm, vec_ok(p.addend, p.ldadd), stg, lane, a);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] += a[j];
+          }
+          if (p.tail && c0 + 16 > p.ncol_main) {
+            // skip-branch columns (>= ncol_main) carry oscale*acc and go to the tail buffer
+            float t[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) t[j] = p.oscale * v[j];
+            const int shift = max(p.ncol_main - c0, 0);       // first tail column inside this block
+            // write columns [shift, min(16, ncol_out - c0)) of t to tail[:, c0 + shift - ncol_main ...]
+            const int ncols = min(16, p.ncol_out - c0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j >= shift && j < ncols && lane < rows_valid) p.tail[size_t(row0 + lane) * p.ldt + (c0 + j - p.ncol_main)] = t[j];
+          }
+          if (cm > 0) store_block16(p.out + size_t(row0) * p.ldo + c0, p.ldo, rows_valid, cm, v_out, stg, lane, r);
+          if constexpr (EPI == EK_TANGENT) {
+            if (cm > 0) {
+              float vv[16];
+              load_block16(p.V + size_t(row0) * p.ldv + c0, p.ldv, rows_valid, cm, vec_ok(p.V, p.ldv), stg, lane, vv);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) vv[j] = 100.0f * (1.0f - s[j]) * vv[j] * v[j];
+              store_block16(p.out2 + size_t(row0) * p.ldo2 + c0, p.ldo2, rows_valid, cm, vec_ok(p.out2, p.ldo2), stg, lane, vv);
             }
           }
         }
@@ -158,12 +270,14 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
     }
   } else if (warp < kEpiWarps + kProdWarps) {
     // ============================== A producers: fp32 HBM -> split bf16 -> swizzled smem
-    const int pw = warp - kEpiWarps;
-    const int rsub = lane >> 4;          // 2 rows per load instruction
-    const int col4 = (lane & 15) * 4;    // 16 lanes x float4 = 64 columns
-    int g = 0;                           // global chunk counter (ring position)
+    const int pw = (warp - kEpiWarps) & 3;       // 32-row slab
+    const int grp = (warp - kEpiWarps) >> 2;     // chunk parity handled by this group
+    const int rsub = lane >> 4;                  // 2 rows per load instruction
+    const int col4 = (lane & 15) * 4;            // 16 lanes x float4 = 64 columns
+    int g = 0;                                   // global chunk counter (ring position)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int c = 0; c < p.k_chunks; ++c, ++g) {
+        if ((g & 1) != grp) continue;
         const int s = g % STAGES;
         float4 x[16];
         const int kcol = c * BK + col4;
@@ -181,14 +295,9 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
         for (int i = 0; i < 16; ++i) {
           const uint32_t r = pw * 32 + i * 2 + rsub;
           const uint32_t off = sw128_offset(r, col4);
-          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(x[i].x, h0, l0); split_bf16(x[i].y, h1, l1);
-          split_bf16(x[i].z, h2, l2); split_bf16(x[i].w, h3, l3);
-          __nv_bfloat162 hh0 = __halves2bfloat162(h0, h1), hh1 = __halves2bfloat162(h2, h3);
-          __nv_bfloat162 ll0 = __halves2bfloat162(l0, l1), ll1 = __halves2bfloat162(l2, l3);
           uint2 hv, lv;
-          hv.x = *reinterpret_cast<uint32_t*>(&hh0); hv.y = *reinterpret_cast<uint32_t*>(&hh1);
-          lv.x = *reinterpret_cast<uint32_t*>(&ll0); lv.y = *reinterpret_cast<uint32_t*>(&ll1);
+          split2(x[i].x, x[i].y, hv.x, lv.x);
+          split2(x[i].z, x[i].w, hv.y, lv.y);
           *reinterpret_cast<uint2*>(a_hi + off) = hv;
           *reinterpret_cast<uint2*>(a_lo + off) = lv;
         }
@@ -197,7 +306,7 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
         if (lane == 0) mbar_arrive(&full[s]);
       }
     }
-  } else if (warp == kEpiWarps + kProdWarps) {
+  } else if (warp == kMmaWarp) {
     // ============================== MMA issuer (one elected lane)
     constexpr uint32_t idesc = make_idesc_bf16(BM, NPAD);
     int g = 0, it = 0;
@@ -247,35 +356,49 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps + kProdWarps + 1) tmem_dealloc<512>(tmem_base);
+  if (warp == kLoadWarp) tmem_dealloc<512>(tmem_base);
 }
 
-template <int NPAD>
+template <int NPAD, int EPI>
 static int launch_linear(const LinearParams& p, cudaStream_t stream) {
   using Cfg = LinCfg<NPAD>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(umma_linear_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(umma_linear_kernel<NPAD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
       return NERO_ERR_CUDA;
     attr_set = true;
   }
   int tiles_cap = (p.m_cap + BM - 1) / BM;
   if (tiles_cap <= 0) return NERO_OK;
   int grid = tiles_cap < kNumSMs ? tiles_cap : kNumSMs;
-  umma_linear_kernel<NPAD><<<grid, kLinearThreads, Cfg::smem_bytes, stream>>>(p);
+  umma_linear_kernel<NPAD, EPI><<<grid, kLinearThreads, Cfg::smem_bytes, stream>>>(p);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }
 
+template <int NPAD>
+static int dispatch_epi(const LinearParams& p, cudaStream_t stream) {
+  if (p.mode == EPI_BIAS_ACT) {
+    if (p.act == ACT_SOFTPLUS100) return launch_linear<NPAD, EK_BIAS_SOFTPLUS>(p, stream);
+    if (p.act == ACT_RELU) return launch_linear<NPAD, EK_BIAS_RELU>(p, stream);
+    return launch_linear<NPAD, EK_BIAS_GENERIC>(p, stream);
+  }
+  if (p.mode == EPI_TANGENT) return launch_linear<NPAD, EK_TANGENT>(p, stream);
+  if (!p.H || p.dact == ACT_NONE) return launch_linear<NPAD, EK_DACT_NONE>(p, stream);
+  if (p.dact == ACT_RELU) return launch_linear<NPAD, EK_DACT_RELU>(p, stream);
+  return launch_linear<NPAD, EK_DACT_SOFTPLUS>(p, stream);
+}
+
 int linear_dispatch(const LinearParams& p, cudaStream_t stream) {
   if (p.k_chunks <= 0 || (p.k_valid & 3) || (p.lda & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15)) return NERO_ERR_ARG;
-  if (p.mode == EPI_TANGENT && (!p.H || !p.V || !p.out2)) return NERO_ERR_ARG;
+  if (p.mode == EPI_TANGENT && (!p.H || !p.V || !p.out2 || p.dact != ACT_SOFTPLUS100)) return NERO_ERR_ARG;
+  if (p.mode == EPI_MUL_DACT && p.dact != ACT_NONE && !p.H) return NERO_ERR_ARG;
   switch (p.n_pad) {
-    case 16: return launch_linear<16>(p, stream);
-    case 64: return launch_linear<64>(p, stream);
-    case 128: return launch_linear<128>(p, stream);
-    case 224: return launch_linear<224>(p, stream);
-    case 256: return launch_linear<256>(p, stream);
+    case 16: return dispatch_epi<16>(p, stream);
+    case 64: return dispatch_epi<64>(p, stream);
+    case 128: return dispatch_epi<128>(p, stream);
+    case 224: return dispatch_epi<224>(p, stream);
+    case 256: return dispatch_epi<256>(p, stream);
     default: return NERO_ERR_ARG;
   }
 }

@@ -1,11 +1,12 @@
 // tcgen05 weight-gradient kernel: dW[n, k] = sum_m dY[m, n] * X[m, k]  (+ sum_m dY2[m, n] * X2[m, k]).
 //
 // The contraction runs over SAMPLES (rows of both fp32 row-major inputs), so both tensor-core operands are
-// transposed on the fly: producer warps read columns of dY / X (coalesced across lanes), split to bf16 hi/lo
-// and write 8-sample k-chunks (one 16-byte store) into the same K-major SWIZZLE_128B layout the linear kernel
-// uses (tile row = feature index, K = sample index).  Split-K over CTAs: CTA p owns a contiguous range of
-// 64-sample chunks, accumulates a 128 x NW fp32 tile in TMEM and writes its partial to HBM; nero_wgrad_finish
-// (k_weights.cu) reduces the partials and applies the weight-norm chain rule.
+// transposed on the fly: 16 producer warps read columns of dY / X (coalesced across lanes), split to bf16 hi/lo
+// (packed cvt.rn.bf16x2) and write 8-sample k-chunks (one 16-byte store, bank-conflict free) into the same
+// K-major SWIZZLE_128B layout the linear kernel uses (tile row = feature index, K = sample index).
+// Split-K over CTAs: CTA (p, t) owns a contiguous range of 64-sample chunks of output row tile t, accumulates a
+// 128 x NW fp32 tile in TMEM and writes its partial to HBM; nero_wgrad_finish (k_weights.cu) reduces the partials
+// and applies the weight-norm chain rule.
 // The optional second pair implements the double-backward term of the SDF network,
 //   dW_k = abar_k^T h_k + v_k^T ubar_k      (SURVEY.md Appendix A.3, K4),
 // in ONE accumulator.  Column sums of dY (bias gradient) are produced by the dY producer threads for free.
@@ -17,7 +18,7 @@ namespace nero {
 struct WgradParams {
   const float* dY; int ldy; const float* X; int ldx;
   const float* dY2; int ldy2; const float* X2; int ldx2;
-  int n0; int n_valid;   // output rows [n0, n0+128) = dY columns; columns >= n_valid read as zero
+  int n0; int n_valid;   // output rows [n0 + 128*blockIdx.y, +128) = dY columns; columns >= n_valid read as zero
   int k0; int k_valid;   // output cols [k0, k0+NW) = X columns; columns >= k_valid read as zero
   float* partial; int ld_partial; int rows_partial;  // [P][rows_partial][ld_partial]
   float* bias_partial;                               // [P][rows_partial] (may be null)
@@ -25,40 +26,52 @@ struct WgradParams {
 };
 
 constexpr int WG_BM = 128, WG_BK = 64;
-constexpr int kWgThreads = 9 * 32;  // warps 0-3: dY producers + epilogue, 4-7: X producers, 8: MMA
+constexpr int kWgProdWarps = 16;
+constexpr int kWgThreads = (kWgProdWarps + 1) * 32;  // warps 0-7: dY producers (0-3 also epilogue), 8-15: X producers, 16: MMA
 constexpr uint32_t kWgABytes = WG_BM * 128;
 
 template <int NW> struct WgCfg {
   static constexpr uint32_t b_plane = NW * 128;
   static constexpr uint32_t stage_bytes = 2 * kWgABytes + 2 * b_plane;
   static constexpr int stages = (stage_bytes * 3 <= 200 * 1024) ? 3 : 2;
-  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 + 256;
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 + 256 + 512;
 };
 
-// one thread transposes 8 consecutive samples of one column into a 16-byte k-chunk (hi and lo planes)
-__device__ __forceinline__ float produce_octet(const float* __restrict__ src, int ld, int col, bool col_ok, int s0, int M,
-                                               uint8_t* plane_hi, uint8_t* plane_lo, uint32_t row, uint32_t octet) {
-  float x[8];
+__device__ __forceinline__ void wg_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+  const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  hi = hb;
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// one thread transposes NOCT x 8 consecutive samples of one column into 16-byte k-chunks (hi and lo planes);
+// all NOCT*8 loads are issued before the first conversion.
+template <int NOCT>
+__device__ __forceinline__ float produce_octets(const float* __restrict__ src, int ld, int col, bool col_ok, int s0, int M,
+                                                uint8_t* plane_hi, uint8_t* plane_lo, uint32_t row, uint32_t oct0) {
+  float x[NOCT][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int s = s0 + i;
-    x[i] = (col_ok && s < M) ? __ldg(src + size_t(s) * ld + col) : 0.0f;
-  }
-  uint32_t hw[4], lw[4];
+  for (int o = 0; o < NOCT; ++o)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int s = s0 + (oct0 + o) * 8 + i;
+      x[o][i] = (col_ok && s < M) ? __ldg(src + size_t(s) * ld + col) : 0.0f;
+    }
   float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(x[2 * i], h0, l0);
-    split_bf16(x[2 * i + 1], h1, l1);
-    __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
-    hw[i] = *reinterpret_cast<uint32_t*>(&hh);
-    lw[i] = *reinterpret_cast<uint32_t*>(&ll);
-    sum += x[2 * i] + x[2 * i + 1];
+  for (int o = 0; o < NOCT; ++o) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wg_split2(x[o][2 * i], x[o][2 * i + 1], hw[i], lw[i]);
+      sum += x[o][2 * i] + x[o][2 * i + 1];
+    }
+    const uint32_t off = row * 128u + (((oct0 + o) ^ (row & 7u)) << 4);
+    *reinterpret_cast<uint4*>(plane_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(plane_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
-  const uint32_t off = row * 128u + ((octet ^ (row & 7u)) << 4);
-  *reinterpret_cast<uint4*>(plane_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-  *reinterpret_cast<uint4*>(plane_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   return sum;
 }
 
@@ -73,61 +86,64 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::stage_bytes + 256);   // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int M = p.m_ptr ? *p.m_ptr : p.m_cap;
   if (M > p.m_cap) M = p.m_cap;
   const int P = gridDim.x;
+  const int n0 = p.n0 + int(blockIdx.y) * WG_BM;
   const int total_chunks = (M + WG_BK - 1) / WG_BK;
   const int cpp = (total_chunks + P - 1) / P;
   const int c_begin = min(total_chunks, int(blockIdx.x) * cpp), c_end = min(total_chunks, c_begin + cpp);
   const int npairs = p.dY2 ? 2 : 1;
-  const int nchunks = (c_end - c_begin) * npairs;
+  const int nc1 = c_end - c_begin;
+  const int nchunks = nc1 * npairs;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kWgProdWarps); mbar_init(&empty[s], 1); }
     mbar_init(tfull, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<256>(tmem_slot);
+  if (threadIdx.x < 128) s_bias[threadIdx.x] = 0.0f;
+  if (warp == kWgProdWarps) tmem_alloc<256>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
-    const bool is_a = warp < 4;
-    const int pw = warp & 3;
+  if (warp < kWgProdWarps) {
+    const bool is_a = warp < 8;
+    const int pw = warp & 3;             // 32-column slab
+    const int oh = (warp >> 2) & 1;      // which half of the 8 octets
     float bias_acc = 0.0f;
     for (int g = 0; g < nchunks; ++g) {
       const int s = g % STAGES;
-      const int pair = g / (c_end - c_begin);
-      const int chunk = c_begin + g % (c_end - c_begin);
+      const int pair = g / nc1;
+      const int chunk = c_begin + g % nc1;
       const int s0 = chunk * WG_BK;
-      mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
       uint8_t* st = smem + s * Cfg::stage_bytes;
       if (is_a) {
         const float* src = pair ? p.dY2 : p.dY;
         const int ld = pair ? p.ldy2 : p.ldy;
         const uint32_t row = pw * 32 + lane;
-        const int col = p.n0 + int(row);
+        const int col = n0 + int(row);
         const bool ok = col < p.n_valid;
-        float sacc = 0.0f;
-#pragma unroll 2
-        for (int o = 0; o < 8; ++o) sacc += produce_octet(src, ld, col, ok, s0 + o * 8, M, st, st + kWgABytes, row, o);
+        mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+        const float sacc = produce_octets<4>(src, ld, col, ok, s0, M, st, st + kWgABytes, row, oh * 4);
         if (pair == 0) bias_acc += sacc;
       } else {
         const float* src = pair ? p.X2 : p.X;
         const int ld = pair ? p.ldx2 : p.ldx;
         uint8_t* bh = st + 2 * kWgABytes;
+        mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
 #pragma unroll 1
         for (int j = 0; j < (NW + 127) / 128; ++j) {
           const uint32_t row = j * 128 + pw * 32 + lane;
           if (row < NW) {
             const int col = p.k0 + int(row);
             const bool ok = col < p.k_valid;
-#pragma unroll 2
-            for (int o = 0; o < 8; ++o) produce_octet(src, ld, col, ok, s0 + o * 8, M, bh, bh + Cfg::b_plane, row, o);
+            produce_octets<4>(src, ld, col, ok, s0, M, bh, bh + Cfg::b_plane, row, oh * 4);
           }
         }
       }
@@ -135,11 +151,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
     }
-    if (is_a) {
+    if (is_a) atomicAdd(&s_bias[pw * 32 + lane], bias_acc);
+    // every producer warp joins the barrier below (named barrier 1) so that s_bias is complete for the epilogue
+    asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
+    if (warp < 4) {
       // -------- epilogue: TMEM -> partial tile in HBM
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
-      const int orow = p.n0 + pw * 32 + lane;
+      const int orow = n0 + pw * 32 + lane;
       float* prow = p.partial + (size_t(blockIdx.x) * p.rows_partial + orow) * p.ld_partial + p.k0;
       const uint32_t taddr = tmem_base + (uint32_t(pw * 32) << 16);
 #pragma unroll 1
@@ -159,7 +178,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
         }
       }
       if (p.bias_partial && p.k0 == 0 && orow < p.rows_partial)
-        p.bias_partial[size_t(blockIdx.x) * p.rows_partial + orow] = bias_acc;
+        p.bias_partial[size_t(blockIdx.x) * p.rows_partial + orow] = s_bias[pw * 32 + lane];
     }
   } else {
     // -------- MMA issuer
@@ -191,11 +210,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<256>(tmem_base);
+  if (warp == kWgProdWarps) tmem_dealloc<256>(tmem_base);
 }
 
 template <int NW>
-static int launch_wgrad(const WgradParams& p, int P, cudaStream_t stream) {
+static int launch_wgrad(const WgradParams& p, int P, int n_tiles, cudaStream_t stream) {
   using Cfg = WgCfg<NW>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -203,26 +222,26 @@ static int launch_wgrad(const WgradParams& p, int P, cudaStream_t stream) {
       return NERO_ERR_CUDA;
     attr_set = true;
   }
-  umma_wgrad_kernel<NW><<<P, kWgThreads, Cfg::smem_bytes, stream>>>(p);
+  umma_wgrad_kernel<NW><<<dim3(P, n_tiles), kWgThreads, Cfg::smem_bytes, stream>>>(p);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }
 
 // Computes partial[P][rows_partial][ld_partial] for output rows [0, n_rows_pad) and columns [0, k_pad)
-// (k_pad multiple of 64), decomposed into 128-row x {256,128,64}-column tiles.
+// (k_pad multiple of 64), decomposed into 128-row tiles (grid.y) x {256,128,64}-column tiles (separate launches).
 int wgrad_dispatch(WgradParams p, int n_rows_pad, int k_pad, int P, cudaStream_t stream) {
   if ((p.ld_partial & 3) || k_pad % 64 || n_rows_pad % 16 || P <= 0) return NERO_ERR_ARG;
-  for (int n0 = 0; n0 < n_rows_pad; n0 += 128) {
-    int k0 = 0;
-    while (k0 < k_pad) {
-      const int rem = k_pad - k0;
-      p.n0 = n0; p.k0 = k0;
-      int rc;
-      if (rem >= 256) { rc = launch_wgrad<256>(p, P, stream); k0 += 256; }
-      else if (rem >= 128) { rc = launch_wgrad<128>(p, P, stream); k0 += 128; }
-      else { rc = launch_wgrad<64>(p, P, stream); k0 += 64; }
-      if (rc != NERO_OK) return rc;
-    }
+  const int n_tiles = (n_rows_pad + 127) / 128;
+  p.n0 = 0;
+  int k0 = 0;
+  while (k0 < k_pad) {
+    const int rem = k_pad - k0;
+    p.k0 = k0;
+    int rc;
+    if (rem >= 256) { rc = launch_wgrad<256>(p, P, n_tiles, stream); k0 += 256; }
+    else if (rem >= 128) { rc = launch_wgrad<128>(p, P, n_tiles, stream); k0 += 128; }
+    else { rc = launch_wgrad<64>(p, P, n_tiles, stream); k0 += 64; }
+    if (rc != NERO_OK) return rc;
   }
   return NERO_OK;
 }

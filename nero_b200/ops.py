@@ -229,7 +229,7 @@ def _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, osc
 
 
 class WgradWorkspace:
-    def __init__(self, device, P=64, rows=256, ld=384):
+    def __init__(self, device, P=74, rows=256, ld=384):
         self.P, self.rows, self.ld = P, rows, ld
         self.partial = torch.zeros(P, rows, ld, dtype=torch.float32, device=device)
         self.bias_partial = torch.zeros(P, rows, dtype=torch.float32, device=device)
