@@ -236,44 +236,41 @@ __global__ void occ_init_kernel(const float* __restrict__ pts, const float* __re
   for (int c = 0; c < 39; ++c) { x0[c] = pe[c]; hc[217 + c] = pe[c] * kInvSqrt2s; }
 }
 
-// candidate mask of the occlusion loss (renderer.py:530-533) and ordered compaction (single block scan over chunks)
+// candidate mask of the occlusion loss (renderer.py:530-533) and compaction: block-local ordered scan + one atomic
+// per block for the base offset (the order across blocks is irrelevant: the loss is a mean over the selected set)
 __global__ void occ_select_kernel(const float* __restrict__ pts, const float* __restrict__ Y8, int ldy, int sdf_col,
                                   const float* __restrict__ G, const int* __restrict__ ray_in, const float* __restrict__ rays_d,
                                   float sdf_thresh, const int* m_ptr, int m_cap, int* sel, int* count) {
-  __shared__ int s_scan[1024];
-  __shared__ int carry;
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
   int M = m_ptr ? *m_ptr : m_cap;
   if (M > m_cap) M = m_cap;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < M; base += 1024) {
-    const int i = base + threadIdx.x;
-    int flag = 0;
-    if (i < M) {
-      const float4 p = *reinterpret_cast<const float4*>(pts + size_t(i) * 4);
-      const float4 g = *reinterpret_cast<const float4*>(G + size_t(i) * 4);
-      const int r = ray_in[i];
-      float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
-      const float dn = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
-      const float nd = (g.x * d[0] + g.y * d[1] + g.z * d[2]) / dn;
-      const float nrm = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
-      flag = (nrm < 0.999f) && (fabsf(Y8[size_t(i) * ldy + sdf_col]) < sdf_thresh) && (nd < 0.f);
-    }
-    s_scan[threadIdx.x] = flag;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = 0;
-      if (threadIdx.x >= o) t = s_scan[threadIdx.x - o];
-      __syncthreads();
-      s_scan[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (flag) sel[carry + s_scan[threadIdx.x] - 1] = i;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += s_scan[1023];
-    __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int flag = 0;
+  if (i < M) {
+    const float4 p = *reinterpret_cast<const float4*>(pts + size_t(i) * 4);
+    const float4 g = *reinterpret_cast<const float4*>(G + size_t(i) * 4);
+    const int r = ray_in[i];
+    float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+    const float dn = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
+    const float nd = (g.x * d[0] + g.y * d[1] + g.z * d[2]) / dn;
+    const float nrm = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+    flag = (nrm < 0.999f) && (fabsf(Y8[size_t(i) * ldy + sdf_col]) < sdf_thresh) && (nd < 0.f);
   }
-  if (threadIdx.x == 0) *count = carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int wcnt = __popc(bal), wrank = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = wcnt;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    s_warp[lane] = incl - v;
+    if (lane == 31) s_base = incl > 0 ? atomicAdd(count, incl) : 0;
+  }
+  __syncthreads();
+  if (flag) sel[s_base + s_warp[warp] + wrank] = i;
 }
 
 // L1 occlusion loss pieces: loss_sum += |occ_prob[sel] - gt| ; docc[sel] = sign(..) (scaled by 1/P on the host side)
@@ -327,7 +324,8 @@ int occ_init(const float* pts, const float* refl, const int* sel, const int* p_p
 int occ_select(const float* pts, const float* Y8, int ldy, int sdf_col, const float* G, const int* ray_in, const float* rays_d,
                float sdf_thresh, const int* m_ptr, int m_cap, int* sel, int* count, cudaStream_t st) {
   if (m_cap <= 0) return NERO_OK;
-  occ_select_kernel<<<1, 1024, 0, st>>>(pts, Y8, ldy, sdf_col, G, ray_in, rays_d, sdf_thresh, m_ptr, m_cap, sel, count);
+  NERO_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+  occ_select_kernel<<<blocks_for(m_cap, 1024), 1024, 0, st>>>(pts, Y8, ldy, sdf_col, G, ray_in, rays_d, sdf_thresh, m_ptr, m_cap, sel, count);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

@@ -144,6 +144,15 @@ __device__ __forceinline__ void store_block16(float* __restrict__ g, int ld, int
   }
   __syncwarp();
 }
+// prefetch the [32 rows x ncols] window of an aux matrix into L2 (one 128-byte line per lane per step)
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ g, int ld, int rows_valid, int ncols, int lane) {
+  if (!g || rows_valid <= 0) return;
+  const int lines = (ncols * 4 + 127) / 128;
+  for (int i = lane; i < rows_valid * lines; i += 32) {
+    const int r = i / lines, l = i % lines;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + size_t(r) * ld + l * 32));
+  }
+}
 __device__ __forceinline__ bool vec_ok(const float* p, int ld) {
   return ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
@@ -191,8 +200,23 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
     const int nmain = kBias ? p.ncol_out : min(p.ncol_out, p.ncol_main);
     const bool v_out = vec_ok(p.out, p.ldo);
     int it = 0;
+    // aux operands (H / addend / V) of the DACT / TANGENT epilogues are pulled into L2 one tile ahead, so the
+    // per-block loads below see L2 latency instead of DRAM latency (each half-warp-group prefetches its own rows once)
+    auto prefetch_tile = [&](int tile) {
+      if constexpr (!kBias) {
+        if (half == 0 && tile < num_tiles) {
+          const int r0 = tile * BM + lg * 32;
+          const int rv = min(32, M - r0);
+          if constexpr (EPI != EK_DACT_NONE) prefetch_rows_l2(p.H ? p.H + size_t(r0) * p.ldh : nullptr, p.ldh, rv, nmain, lane);
+          prefetch_rows_l2(p.addend ? p.addend + size_t(r0) * p.ldadd : nullptr, p.ldadd, rv, nmain, lane);
+          if constexpr (EPI == EK_TANGENT) prefetch_rows_l2(p.V + size_t(r0) * p.ldv, p.ldv, rv, nmain, lane);
+        }
+      }
+    };
+    prefetch_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
+      prefetch_tile(tile + gridDim.x);
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tcgen05_fence_after();
       const int row0 = tile * BM + lg * 32;

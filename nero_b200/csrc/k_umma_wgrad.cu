@@ -46,12 +46,11 @@ __device__ __forceinline__ void wg_split2(float x0, float x1, uint32_t& hi, uint
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-// one thread transposes NOCT x 8 consecutive samples of one column into 16-byte k-chunks (hi and lo planes);
-// all NOCT*8 loads are issued before the first conversion.
+// one thread transposes NOCT x 8 consecutive samples of one column into 16-byte k-chunks (hi and lo planes).
+// load_octets issues all NOCT*8 loads (before the smem slot is known to be free); store_octets converts and stores.
 template <int NOCT>
-__device__ __forceinline__ float produce_octets(const float* __restrict__ src, int ld, int col, bool col_ok, int s0, int M,
-                                                uint8_t* plane_hi, uint8_t* plane_lo, uint32_t row, uint32_t oct0) {
-  float x[NOCT][8];
+__device__ __forceinline__ void load_octets(const float* __restrict__ src, int ld, int col, bool col_ok, int s0, int M, uint32_t oct0,
+                                            float (&x)[NOCT][8]) {
 #pragma unroll
   for (int o = 0; o < NOCT; ++o)
 #pragma unroll
@@ -59,6 +58,9 @@ __device__ __forceinline__ float produce_octets(const float* __restrict__ src, i
       const int s = s0 + (oct0 + o) * 8 + i;
       x[o][i] = (col_ok && s < M) ? __ldg(src + size_t(s) * ld + col) : 0.0f;
     }
+}
+template <int NOCT>
+__device__ __forceinline__ float store_octets(const float (&x)[NOCT][8], uint8_t* plane_hi, uint8_t* plane_lo, uint32_t row, uint32_t oct0) {
   float sum = 0.0f;
 #pragma unroll
   for (int o = 0; o < NOCT; ++o) {
@@ -129,22 +131,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
         const uint32_t row = pw * 32 + lane;
         const int col = n0 + int(row);
         const bool ok = col < p.n_valid;
+        float x[4][8];
+        load_octets<4>(src, ld, col, ok, s0, M, oh * 4, x);
         mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
-        const float sacc = produce_octets<4>(src, ld, col, ok, s0, M, st, st + kWgABytes, row, oh * 4);
+        const float sacc = store_octets<4>(x, st, st + kWgABytes, row, oh * 4);
         if (pair == 0) bias_acc += sacc;
       } else {
         const float* src = pair ? p.X2 : p.X;
         const int ld = pair ? p.ldx2 : p.ldx;
         uint8_t* bh = st + 2 * kWgABytes;
-        mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
-#pragma unroll 1
-        for (int j = 0; j < (NW + 127) / 128; ++j) {
+        constexpr int NJ = (NW + 127) / 128;
+        float x[NJ][4][8];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
           const uint32_t row = j * 128 + pw * 32 + lane;
-          if (row < NW) {
-            const int col = p.k0 + int(row);
-            const bool ok = col < p.k_valid;
-            produce_octets<4>(src, ld, col, ok, s0, M, bh, bh + Cfg::b_plane, row, oh * 4);
-          }
+          const int col = p.k0 + int(row);
+          load_octets<4>(src, ld, col, row < NW && col < p.k_valid, s0, M, oh * 4, x[j]);
+        }
+        mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const uint32_t row = j * 128 + pw * 32 + lane;
+          if (row < NW) store_octets<4>(x[j], bh, bh + Cfg::b_plane, row, oh * 4);
         }
       }
       fence_proxy_async_smem();

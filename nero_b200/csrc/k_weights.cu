@@ -81,8 +81,16 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, in
   const int r = blockIdx.x, n = row0 + r;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const int kc = kmap ? kmap[k] : k;
-    float acc = 0.0f;
-    for (int pidx = 0; pidx < P; ++pidx) acc += partial[(size_t(pidx) * rows_partial + r) * ld_partial + kc];
+    const float* pp = partial + size_t(r) * ld_partial + kc;
+    const size_t pstride = size_t(rows_partial) * ld_partial;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int pidx = 0;
+    for (; pidx + 3 < P; pidx += 4) {   // 4 independent partial sums: the loads of one row are latency bound
+      a0 += pp[size_t(pidx) * pstride]; a1 += pp[size_t(pidx + 1) * pstride];
+      a2 += pp[size_t(pidx + 2) * pstride]; a3 += pp[size_t(pidx + 3) * pstride];
+    }
+    for (; pidx < P; ++pidx) a0 += pp[size_t(pidx) * pstride];
+    float acc = (a0 + a1) + (a2 + a3);
     acc *= in_scale;
     if (extra_row && r == 0) acc += extra_scale * extra_row[kc];
     s_dw[k] = acc;
@@ -114,7 +122,7 @@ int wgrad_finish(const float* partial, int P, int rows_partial, int ld_partial, 
                  int row0, int nrows, const int* kmap, float in_scale, const float* v, const float* g, float* grad_w,
                  float* grad_g, float* grad_b, const float* extra_row, float extra_scale, cudaStream_t stream) {
   if (nrows <= 0) return NERO_OK;
-  wgrad_finish_kernel<<<nrows, 128, K * sizeof(float), stream>>>(partial, P, rows_partial, ld_partial, bias_partial, K, row0,
+  wgrad_finish_kernel<<<nrows, 256, K * sizeof(float), stream>>>(partial, P, rows_partial, ld_partial, bias_partial, K, row0,
                                                                  kmap, in_scale, v, g, grad_w, grad_g, grad_b, extra_row,
                                                                  extra_scale);
   NERO_LAUNCH_CHECK();

@@ -129,6 +129,7 @@ class NeROShapeRenderer(nn.Module):
         torch in the reference's order (renderer.py:416, :422) unless passed in."""
         e = self.engine
         e.prepare_weights()
+        self._weights_fresh = True      # consumed by the render_core call that follows in render()
         R = rays_o.shape[0]
         if perturb > 0 and rand_inner is None:
             rand_inner = torch.rand([R, 1], device=rays_o.device)
@@ -146,6 +147,9 @@ class NeROShapeRenderer(nn.Module):
         e = self.engine
         if step < 1000:
             raise NotImplementedError('init_sdf_reg outputs (step < 1000) are not implemented in the B200 path yet')
+        if not getattr(self, '_weights_fresh', False):
+            e.prepare_weights()          # render_core called on its own: fold weight-norm / rebuild operand images
+        self._weights_fresh = False
         params = [p for p in self.parameters()]
         rgb, gerr, loss_occ = _RenderCoreFn.apply(e, rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(),
                                                   human_poses.contiguous(), float(cos_anneal_ratio), int(step), perm, *params)
