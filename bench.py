@@ -296,8 +296,6 @@ def cpu_baseline(rays_n=128, steps=1, threads=None):
     step (sample_ray + render_core + loss + backward) on a bounded sample of the same workload."""
     import nero_oracle as O
     from nero_b200 import params as P
-    cores = threads or os.cpu_count()
-    torch.set_num_threads(cores)
     cfg = {}
     sd = O.perturb_params(P.build_shape_state_dict(cfg, seed=6033))
     rays = O.synthetic_rays(rays_n, seed=6033)
@@ -312,6 +310,29 @@ def cpu_baseline(rays_n=128, steps=1, threads=None):
         out = O.render(p, cfg, lut, rays['rays_o'], rays['rays_d'], rays['near'], rays['far'], rays['human_poses'], car, STEP,
                        rand_inner=ri, rand_bg=rb)
         O.training_loss(out, rays['rgb'], c, STEP).backward()
+    # "all the host threads it can use": torch's intra-op pool is slower when oversubscribed on these small ops, so
+    # pick the best of a few pool sizes on a short calibration slice and report the count actually used
+    ncpu = os.cpu_count() or 1
+    cands = [threads] if threads else sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    if len(cands) > 1:
+        full_n, rays_cal = rays_n, max(16, rays_n // 8)
+        best = None
+        for c_ in cands:
+            torch.set_num_threads(c_)
+            rays_n = rays_cal
+            rays_save = rays
+            rays = {k: v[:rays_cal] for k, v in rays_save.items()}
+            one()
+            t0 = time.time()
+            one()
+            dt_c = time.time() - t0
+            rays, rays_n = rays_save, full_n
+            if best is None or dt_c < best[0]:
+                best = (dt_c, c_)
+        cores = best[1]
+    else:
+        cores = cands[0]
+    torch.set_num_threads(cores)
     one()   # warm-up
     t0 = time.time()
     for _ in range(steps):

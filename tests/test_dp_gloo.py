@@ -1,0 +1,72 @@
+"""World-size-2 gloo test of the data-parallel host logic (nero_b200/dp.py) on CPU: two ranks run the ORACLE on their
+ray shards, rescale the eikonal mean with dp.global_mean_weight, average flat gradients with dp.sync_gradients, and
+must reproduce the single-process gradient of the whole batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import nero_oracle as O
+from helpers import build_params
+from nero_b200 import dp
+
+CFG = {'n_samples': 16, 'n_importance': 16, 'n_bg_samples': 8, 'up_sample_steps': 2}
+STEP = 10000
+
+
+def _loss_and_grads(sd, rays, sl, eik_scale_fn):
+    p = {k: v.clone().requires_grad_(torch.is_floating_point(v) and not k.endswith('FG_LUT')) for k, v in sd.items()}
+    c = O.merged_cfg(CFG)
+    lut = sd['color_network.FG_LUT'][0]
+    r = {k: v[sl] for k, v in rays.items()}
+    out = O.render(p, CFG, lut, r['rays_o'], r['rays_d'], r['near'], r['far'], r['human_poses'], O.get_anneal_val(c, STEP), STEP)
+    n_in = out['gradient_error'].numel()
+    loss = torch.mean(O.compute_rgb_loss(out['ray_rgb'], r['rgb'])) + eik_scale_fn(n_in) * torch.mean(out['gradient_error'] * 0.1)
+    loss.backward()
+    names = sorted(k for k in p if p[k].grad is not None)
+    return torch.cat([p[k].grad.reshape(-1) for k in names]), n_in
+
+
+def _worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    sd = build_params(CFG)
+    rays = O.synthetic_rays(16, seed=3)
+    flat, n_in = _loss_and_grads(sd, rays, dp.shard_slice(16, rank, world), lambda n: dp.global_mean_weight(n, world))
+    dp.sync_gradients(flat, world)
+    if rank == 0:
+        q.put(flat.numpy())
+    dist.destroy_process_group()
+
+
+def test_ray_sharded_dp_matches_single_process():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    got = q.get(timeout=300)
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    torch.set_num_threads(4)
+    sd = build_params(CFG)
+    rays = O.synthetic_rays(16, seed=3)
+    want, _ = _loss_and_grads(sd, rays, slice(0, 16), lambda n: 1.0)
+    want = want.numpy()
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-8
+
+
+def test_shard_slices_cover_batch():
+    idx = np.concatenate([np.arange(64)[dp.shard_slice(64, r, 4)] for r in range(4)])
+    assert (idx == np.arange(64)).all()
