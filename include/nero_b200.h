@@ -52,6 +52,29 @@ int nero_linear(const float* A, int lda, int k_valid, const void* wimg, int n_pa
                 const float* addend, int ldadd, int ncol_main, float* tail, int ldt,
                 const int* m_ptr, int m_cap, void* stream);
 
+/* ---- fused MLP chain on tcgen05 (A operand kept in TMEM across layers) ------------------------------------------
+ * Runs up to 10 consecutive layers of SDFNetwork / make_predictor / NeRFNetwork (network/field.py:130-147, 310-346,
+ * 258-283) or of their gradient sweeps on each 128-row tile without writing the inter-layer activations' A operand
+ * to HBM.  `chain_params_host` points to a HOST struct nero_chain_params (layout below, natural alignment). */
+typedef struct nero_chain_layer {
+  const void* wimg; const float* bias;
+  float* save; const float* H; const float* addend; const float* V; float* out2; float* tail;
+  int n_pad, k_chunks, n_bias, ncol_out, ncol_main, kind, act;   /* kind: 0 bias+softplus100, 1 bias+relu, 2 bias+act(generic), */
+  int ld_save, ldh, ldadd, ldv, ldo2, ldt;                        /*       3 dsoftplus*acc, 4 drelu*acc, 5 acc, 6 tangent        */
+  float oscale, hscale, act_param;
+  int write_a, a_blocks;
+  const float* csrc; int ld_csrc;
+  int pad_;
+} nero_chain_layer;
+typedef struct nero_chain_params {
+  const float* A0; int lda0; int k_valid0;
+  int n_layers; const int* m_ptr; int m_cap;
+  nero_chain_layer L[10];
+} nero_chain_params;
+int nero_chain(const void* chain_params_host, void* stream);
+/* Y[i,:] += a[i*lda] * X[i,:] */
+int nero_row_axpy(const float* a, int lda, const float* X, int ldx, float* Y, int ldy, int ncol, const int* m_ptr, int m_cap, void* stream);
+
 /* ---- weight gradients -------------------------------------------------------------------------------------
  * partial[p] = dY^T X (+ dY2^T X2) over the p-th slice of rows; replaces the autograd weight-gradient GEMMs. */
 int nero_wgrad(const float* dY, int ldy, int n_valid, const float* X, int ldx, int k_valid,

@@ -160,6 +160,21 @@ __global__ void dact_times_row_kernel(const float* __restrict__ H, int ldh, cons
   }
 }
 
+// Y[i,:] += a[i*lda] * X[i,:]        (abar_7 += dsdf * v_7: the sdf-row term of the value backward)
+__global__ void row_axpy_kernel(const float* __restrict__ a, int lda, const float* __restrict__ X, int ldx, float* Y, int ldy,
+                                int ncol, const int* m_ptr, int m_cap) {
+  const int M = load_count(m_ptr, m_cap);
+  const size_t total = size_t(M) * (ncol / 4);
+  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+    const int i = int(idx / (ncol / 4)), j = int(idx % (ncol / 4)) * 4;
+    const float s = a[size_t(i) * lda];
+    const float4 x = *reinterpret_cast<const float4*>(X + size_t(i) * ldx + j);
+    float4 y = *reinterpret_cast<float4*>(Y + size_t(i) * ldy + j);
+    y.x += s * x.x; y.y += s * x.y; y.z += s * x.z; y.w += s * x.w;
+    *reinterpret_cast<float4*>(Y + size_t(i) * ldy + j) = y;
+  }
+}
+
 // g = J_PE^T (U0 + USKIP)
 __global__ void pe_grad_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ U0, int ldu,
                                const float* __restrict__ US, int lds, float* G, const int* m_ptr, int m_cap) {
@@ -350,6 +365,13 @@ int ray_fill(const FillParams& q, cudaStream_t st) {
 int dact_times_row(const float* H, int ldh, const float* row, float* V, int ldv, int ncol, const int* m_ptr, int m_cap, cudaStream_t st) {
   if (m_cap <= 0) return NERO_OK;
   dact_times_row_kernel<<<kNumSMs * 8, 256, 0, st>>>(H, ldh, row, V, ldv, ncol, m_ptr, m_cap);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+int row_axpy(const float* a, int lda, const float* X, int ldx, float* Y, int ldy, int ncol, const int* m_ptr, int m_cap, cudaStream_t st) {
+  if (m_cap <= 0) return NERO_OK;
+  if ((ncol & 3) || (ldx & 3) || (ldy & 3)) return NERO_ERR_ARG;
+  row_axpy_kernel<<<kNumSMs * 8, 256, 0, st>>>(a, lda, X, ldx, Y, ldy, ncol, m_ptr, m_cap);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

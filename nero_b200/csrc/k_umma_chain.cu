@@ -1,0 +1,325 @@
+// Fused MLP-CHAIN kernel on tcgen05: a 128-row tile of samples flows through a whole sequence of linear layers
+// without its activations ever leaving the SM between layers.
+//
+//   TMEM (512 columns x 128 lanes x 32 bit, all of it):
+//     [  0,256)  fp32 accumulator of the current layer (D operand)
+//     [256,384)  A operand, bf16 "hi" plane, two K elements per 32-bit column  (A read by tcgen05.mma FROM TMEM)
+//     [384,512)  A operand, bf16 "lo" plane                                    (split-bf16: x ~= hi + lo)
+//   Per layer: the MMA warp issues, per 16-wide k-step, A_lo*W_hi + A_hi*W_lo + A_hi*W_hi into the accumulator;
+//   twelve epilogue warps then read the accumulator (tcgen05.ld), apply bias/activation or the derivative products
+//   of the gradient sweeps, store what the backward pass needs to HBM (coalesced through a per-warp transpose
+//   buffer) and write the NEXT layer's A operand straight back into TMEM (tcgen05.st) as packed split-bf16.
+//   Weights stream from L2 as pre-swizzled images (one cp.async.bulk per 64-wide K chunk, 3-stage mbarrier ring).
+//   Aux operands of the derivative epilogues (H, addend, V) are prefetched into L2 one layer ahead.
+//
+// This realises SURVEY.md K2/K3/K4/K10/K13 "activations stay on-chip across layers": compared with one
+// nero_linear launch per layer it removes the A-operand HBM round trip (1 KB/sample/layer) and the producer
+// load->convert->store latency chain, which the ncu profiles of round 1 (profiles/r01b_*) show to dominate.
+//
+// Skip connection of the SDF network (field.py:139-140): a layer with `concat` set takes columns >= ncol_out of the
+// next A operand from its own `save` buffer, where ray_fill / pe_tangent pre-stored PE/sqrt2 resp. its tangent.
+#include "umma_common.cuh"
+
+namespace nero {
+
+constexpr int kMaxChainLayers = 10;
+
+struct ChainLayer {
+  const uint8_t* wimg; const float* bias;
+  float* save; const float* H; const float* addend; const float* V; float* out2; float* tail;
+  int n_pad, k_chunks, n_bias, ncol_out, ncol_main, kind, act;
+  int ld_save, ldh, ldadd, ldv, ldo2, ldt;
+  float oscale, hscale, act_param;
+  int write_a, a_blocks;      // write_a: the output becomes the next A operand; a_blocks: 16-col blocks of it to define
+  const float* csrc; int ld_csrc;   // skip-concat source: columns >= ncol_out of the next A operand come from csrc[row, col]
+  int pad_;
+};
+struct ChainParams {
+  const float* A0; int lda0; int k_valid0;
+  int n_layers; const int* m_ptr; int m_cap;
+  ChainLayer L[kMaxChainLayers];
+};
+
+constexpr int CH_BM = 128, CH_BK = 64;
+constexpr int kChEpiWarps = 12;
+constexpr int kChMmaWarp = kChEpiWarps, kChLoadWarp = kChEpiWarps + 1;
+constexpr int kChThreads = (kChEpiWarps + 2) * 32;
+constexpr int kChStages = 3;
+constexpr uint32_t kChStageBytes = 2 * 256 * 128;                       // W chunk: hi + lo planes of up to 256 rows
+constexpr uint32_t kChEpiBytes = kChEpiWarps * kStageWarpBytes;         // 30 KB
+constexpr uint32_t kChSmemBytes = kChStages * kChStageBytes + kChEpiBytes + 1024 + 256;
+constexpr uint32_t kAccCol = 0, kAHiCol = 256, kALoCol = 384;
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// write 16 fp32 values of this lane's row (columns c0..c0+15 of the next A operand) as packed split-bf16 into TMEM
+__device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const float* y) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+  tmem_st8(tmem_lane_base + kAHiCol + (c0 >> 1), hi);
+  tmem_st8(tmem_lane_base + kALoCol + (c0 >> 1), lo);
+}
+
+template <int KIND>
+__device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32_t tmem_lane_base, int row0, int rows_valid,
+                                                     int third, int lane, float* stg) {
+  constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
+  const int nblk = L.n_pad >> 4;
+  const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
+  const bool v_save = L.save && vec_ok(L.save, L.ld_save);
+  // when this layer feeds the next one, every 16-column block the next layer's MMAs read must be defined
+  const int nblk_a = L.write_a ? max(L.a_blocks, nblk) : 0;
+  const int nb_loop = max(nblk, nblk_a);
+#pragma unroll 1
+  for (int b = third; b < nb_loop; b += 3) {
+    const int c0 = b * 16;
+    float r[16];
+    if (b < nblk && c0 < L.ncol_out) {
+      float v[16];
+      tmem_ld16(tmem_lane_base + kAccCol + c0, v);
+      tmem_ld_wait();
+      if constexpr (kBias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          const float x = v[j] + ((L.bias && col < L.n_bias) ? __ldg(L.bias + col) : 0.0f);
+          float y;
+          if constexpr (KIND == EK_BIAS_SOFTPLUS) y = softplus100_fast(x);
+          else if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(x, 0.0f);
+          else y = apply_act(x, L.act, L.act_param);
+          r[j] = L.oscale * y;
+        }
+      } else {
+        const int cm = nmain - c0;
+        float s[16];
+        if constexpr (KIND == EK_DACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s[j] = 1.0f;
+        } else {
+          load_block16(L.H + size_t(row0) * L.ldh + c0, L.ldh, rows_valid, cm, vec_ok(L.H, L.ldh), stg, lane, s);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (KIND == EK_DACT_RELU) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
+            else s[j] = dsoftplus100_from_h_fast(s[j] * L.hscale);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = L.oscale * s[j] * v[j];
+        if (L.addend) {
+          float a[16];
+          load_block16(L.addend + size_t(row0) * L.ldadd + c0, L.ldadd, rows_valid, cm, vec_ok(L.addend, L.ldadd), stg, lane, a);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] += a[j];
+        }
+        if (L.tail && c0 + 16 > L.ncol_main) {
+          const int shift = max(L.ncol_main - c0, 0);
+          const int ncols = min(16, L.ncol_out - c0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j >= shift && j < ncols && lane < rows_valid)
+              L.tail[size_t(row0 + lane) * L.ldt + (c0 + j - L.ncol_main)] = L.oscale * v[j];
+        }
+        if constexpr (KIND == EK_TANGENT) {
+          if (cm > 0) {
+            float vv[16];
+            load_block16(L.V + size_t(row0) * L.ldv + c0, L.ldv, rows_valid, cm, vec_ok(L.V, L.ldv), stg, lane, vv);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vv[j] = 100.0f * (1.0f - s[j]) * vv[j] * v[j];
+            store_block16(L.out2 + size_t(row0) * L.ldo2 + c0, L.ldo2, rows_valid, cm, vec_ok(L.out2, L.ldo2), stg, lane, vv);
+          }
+        }
+      }
+      if (L.save && nmain - c0 > 0) store_block16(L.save + size_t(row0) * L.ld_save + c0, L.ld_save, rows_valid, nmain - c0, v_save, stg, lane, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = 0.0f;
+    }
+    if (b < nblk_a) {
+      // columns >= nmain of the next A operand: the skip-concat source (from the save buffer) or zero
+      if (c0 + 16 > nmain) {
+        float cc[16];
+        if (L.csrc) load_block16(L.csrc + size_t(row0) * L.ld_csrc + c0, L.ld_csrc, rows_valid, 256 - c0, vec_ok(L.csrc, L.ld_csrc), stg, lane, cc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j >= nmain) r[j] = L.csrc ? cc[j] : 0.0f;
+      }
+      write_a16(tmem_lane_base, c0, r);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_epi = reinterpret_cast<float*>(smem + kChStages * kChStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChStages * kChStageBytes + kChEpiBytes);
+  uint64_t* full = bars;                        // [stages]  W chunk landed
+  uint64_t* empty = bars + kChStages;           // [stages]  W chunk consumed
+  uint64_t* a_ready = bars + 2 * kChStages;     // A operand written + accumulator drained (12 epilogue warps)
+  uint64_t* acc_ready = bars + 2 * kChStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kChStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int M = p.m_ptr ? *p.m_ptr : p.m_cap;
+  if (M > p.m_cap) M = p.m_cap;
+  const int num_tiles = (M + CH_BM - 1) / CH_BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kChStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_ready, kChEpiWarps);
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == kChLoadWarp) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kChEpiWarps) {
+    // ============================== epilogue warps
+    const int lg = warp & 3, third = warp >> 2;
+    float* stg = s_epi + warp * (32 * kStagePitch);
+    const uint32_t tl = tmem_base + (uint32_t(lg * 32) << 16);
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int row0 = tile * CH_BM + lg * 32;
+      const int rows_valid = min(32, M - row0);
+      // ---- first A operand: fp32 rows from HBM -> split-bf16 in TMEM
+      {
+        const bool v0 = vec_ok(p.A0, p.lda0);
+        const int nb0 = p.L[0].k_chunks * 4;      // every column the first layer's MMAs read (zeros beyond k_valid0)
+        for (int b = third; b < nb0; b += 3) {
+          float x[16];
+          load_block16(p.A0 + size_t(row0) * p.lda0 + b * 16, p.lda0, rows_valid, p.k_valid0 - b * 16, v0, stg, lane, x);
+          write_a16(tl, b * 16, x);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+      for (int l = 0; l < p.n_layers; ++l) {
+        const ChainLayer& L = p.L[l];
+        // prefetch the aux operands of THIS layer's epilogue into L2 while the MMAs run
+        if (third == 0 && rows_valid > 0 && L.kind >= EK_DACT_SOFTPLUS) {
+          const int nm = min(L.ncol_out, L.ncol_main);
+          if (L.kind != EK_DACT_NONE) prefetch_rows_l2(L.H + size_t(row0) * L.ldh, L.ldh, rows_valid, nm, lane);
+          prefetch_rows_l2(L.addend ? L.addend + size_t(row0) * L.ldadd : nullptr, L.ldadd, rows_valid, nm, lane);
+          if (L.kind == EK_TANGENT) prefetch_rows_l2(L.V + size_t(row0) * L.ldv, L.ldv, rows_valid, nm, lane);
+        }
+        mbar_wait(acc_ready, acc_phase);
+        acc_phase ^= 1;
+        tcgen05_fence_after();
+        switch (L.kind) {
+          case EK_BIAS_SOFTPLUS: chain_epilogue_layer<EK_BIAS_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg); break;
+          case EK_BIAS_RELU: chain_epilogue_layer<EK_BIAS_RELU>(L, tl, row0, rows_valid, third, lane, stg); break;
+          case EK_BIAS_GENERIC: chain_epilogue_layer<EK_BIAS_GENERIC>(L, tl, row0, rows_valid, third, lane, stg); break;
+          case EK_DACT_SOFTPLUS: chain_epilogue_layer<EK_DACT_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg); break;
+          case EK_DACT_RELU: chain_epilogue_layer<EK_DACT_RELU>(L, tl, row0, rows_valid, third, lane, stg); break;
+          case EK_DACT_NONE: chain_epilogue_layer<EK_DACT_NONE>(L, tl, row0, rows_valid, third, lane, stg); break;
+          default: chain_epilogue_layer<EK_TANGENT>(L, tl, row0, rows_valid, third, lane, stg); break;
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        // the last layer of the last tile has no consumer, every other (tile, layer) hands over to the MMA warp
+        if (lane == 0 && l + 1 < p.n_layers) mbar_arrive(a_ready);
+      }
+    }
+  } else if (warp == kChMmaWarp) {
+    // ============================== MMA issuer
+    int g = 0;
+    uint32_t a_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int l = 0; l < p.n_layers; ++l) {
+        const ChainLayer& L = p.L[l];
+        const uint32_t idesc = make_idesc_bf16(CH_BM, uint32_t(L.n_pad));
+        const uint32_t b_plane = uint32_t(L.n_pad) * 128u;
+        mbar_wait(a_ready, a_phase);
+        a_phase ^= 1;
+        tcgen05_fence_after();
+        for (int c = 0; c < L.k_chunks; ++c, ++g) {
+          const int s = g % kChStages;
+          mbar_wait(&full[s], (g / kChStages) & 1);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t b_hi = smem_u32(smem + s * kChStageBytes);
+            const uint32_t b_lo = b_hi + b_plane;
+#pragma unroll
+            for (int k = 0; k < CH_BK / 16; ++k) {
+              const uint32_t a_col = uint32_t(c * 32 + k * 8);
+              const uint64_t dbh = make_desc_k_sw128(b_hi + k * 32), dbl = make_desc_k_sw128(b_lo + k * 32);
+              umma_bf16_ts(tmem_base + kAccCol, tmem_base + kALoCol + a_col, dbh, idesc, (c | k) != 0);
+              umma_bf16_ts(tmem_base + kAccCol, tmem_base + kAHiCol + a_col, dbl, idesc, 1);
+              umma_bf16_ts(tmem_base + kAccCol, tmem_base + kAHiCol + a_col, dbh, idesc, 1);
+            }
+            umma_commit(&empty[s]);
+            if (c == L.k_chunks - 1) umma_commit(acc_ready);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ============================== W loader
+    int g = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int l = 0; l < p.n_layers; ++l) {
+        const ChainLayer& L = p.L[l];
+        const uint32_t bytes = 2u * uint32_t(L.n_pad) * 128u;
+        for (int c = 0; c < L.k_chunks; ++c, ++g) {
+          const int s = g % kChStages;
+          mbar_wait(&empty[s], ((g / kChStages) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_copy_g2s(smem + s * kChStageBytes, L.wimg + size_t(c) * bytes, bytes, &full[s]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kChLoadWarp) tmem_dealloc<512>(tmem_base);
+}
+
+int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
+  if (p.n_layers <= 0 || p.n_layers > kMaxChainLayers || (p.lda0 & 3) || p.k_valid0 > 256) return NERO_ERR_ARG;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const ChainLayer& L = p.L[l];
+    if (L.n_pad % 16 || L.n_pad < 16 || L.n_pad > 256 || L.k_chunks < 1 || L.k_chunks > 4 || L.ncol_out > L.n_pad) return NERO_ERR_ARG;
+    if (L.kind == EK_TANGENT && (!L.H || !L.V || !L.out2)) return NERO_ERR_ARG;
+    if ((L.kind == EK_DACT_SOFTPLUS || L.kind == EK_DACT_RELU) && !L.H) return NERO_ERR_ARG;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes) != cudaSuccess) return NERO_ERR_CUDA;
+    attr_set = true;
+  }
+  const int tiles_cap = (p.m_cap + CH_BM - 1) / CH_BM;
+  if (tiles_cap <= 0) return NERO_OK;
+  const int grid = tiles_cap < kNumSMs ? tiles_cap : kNumSMs;
+  umma_chain_kernel<<<grid, kChThreads, kChSmemBytes, stream>>>(p);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
+}  // namespace nero

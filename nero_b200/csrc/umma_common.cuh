@@ -1,0 +1,113 @@
+// Device helpers shared by the tcgen05 GEMM kernels (k_umma_linear.cu, k_umma_chain.cu).
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nero {
+
+// compile-time epilogue kinds
+enum EpiKind : int { EK_BIAS_SOFTPLUS = 0, EK_BIAS_RELU = 1, EK_BIAS_GENERIC = 2, EK_DACT_SOFTPLUS = 3, EK_DACT_RELU = 4,
+                     EK_DACT_NONE = 5, EK_TANGENT = 6 };
+
+constexpr int kStagePitch = 20;                  // floats per row of the per-warp transpose buffer (16 cols + pad)
+constexpr uint32_t kStageWarpBytes = 32 * kStagePitch * 4;
+
+// fast softplus(beta=100): max error ~1e-9 absolute (ex2/lg2 approximations, 1+t rounding)
+__device__ __forceinline__ float softplus100_fast(float a) {
+  const float z = 100.0f * a;
+  const float t = exp2f(fminf(z, 20.0f) * 1.4426950408889634f);      // MUFU.EX2
+  const float h = __log2f(1.0f + t) * (0.6931471805599453f * 0.01f);  // MUFU.LG2
+  return z > 20.0f ? a : h;
+}
+__device__ __forceinline__ float dsoftplus100_from_h_fast(float h) {
+  const float z = 100.0f * h;
+  return z > 20.0f ? 1.0f : 1.0f - exp2f(-z * 1.4426950408889634f);
+}
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
+  const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  hi = hb;
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// 16 columns of one TMEM lane group
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// coalesced load of a [32 rows x 16 cols] block (row-major global, leading dim ld) into registers of the
+// "lane = row" layout, through the warp's transpose buffer.  Rows >= rows_valid / cols >= cols_valid read as 0.
+__device__ __forceinline__ void load_block16(const float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec,
+                                             float* stage, int lane, float* r) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid) {
+      const float* p = g + size_t(row) * ld + q;
+      if (vec && q + 3 < cols_valid) x = *reinterpret_cast<const float4*>(p);
+      else {
+        if (q < cols_valid) x.x = p[0];
+        if (q + 1 < cols_valid) x.y = p[1];
+        if (q + 2 < cols_valid) x.z = p[2];
+        if (q + 3 < cols_valid) x.w = p[3];
+      }
+    }
+    *reinterpret_cast<float4*>(stage + row * kStagePitch + q) = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 x = *reinterpret_cast<const float4*>(stage + lane * kStagePitch + j * 4);
+    r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
+  }
+  __syncwarp();
+}
+// the reverse: registers ("lane = row") -> coalesced global store of columns [0, cols_valid)
+__device__ __forceinline__ void store_block16(float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec,
+                                              float* stage, int lane, const float* r) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4*>(stage + lane * kStagePitch + j * 4) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+    if (row < rows_valid && q < cols_valid) {
+      const float4 x = *reinterpret_cast<const float4*>(stage + row * kStagePitch + q);
+      float* p = g + size_t(row) * ld + q;
+      if (vec && q + 3 < cols_valid) *reinterpret_cast<float4*>(p) = x;
+      else {
+        p[0] = x.x;
+        if (q + 1 < cols_valid) p[1] = x.y;
+        if (q + 2 < cols_valid) p[2] = x.z;
+        if (q + 3 < cols_valid) p[3] = x.w;
+      }
+    }
+  }
+  __syncwarp();
+}
+// prefetch the [32 rows x ncols] window of an aux matrix into L2 (one 128-byte line per lane per step)
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ g, int ld, int rows_valid, int ncols, int lane) {
+  if (!g || rows_valid <= 0) return;
+  const int lines = (ncols * 4 + 127) / 128;
+  for (int i = lane; i < rows_valid * lines; i += 32) {
+    const int r = i / lines, l = i % lines;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + size_t(r) * ld + l * 32));
+  }
+}
+__device__ __forceinline__ bool vec_ok(const float* p, int ld) {
+  return ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+
+}  // namespace nero

@@ -19,7 +19,10 @@ import numpy as np
 import torch
 
 from . import ops
-from .ops import Mat, K, linear, wgrad, ACT_NONE, ACT_SOFTPLUS100, ACT_RELU, ACT_SIGMOID, ACT_EXPCLAMP, EPI_MUL_DACT, EPI_TANGENT
+from .ops import Mat, K, linear, wgrad, chain, chain_layer as CL, ACT_NONE, ACT_SOFTPLUS100, ACT_RELU, ACT_SIGMOID, ACT_EXPCLAMP, EPI_MUL_DACT, EPI_TANGENT
+from .ops import EK_BIAS_SOFTPLUS, EK_BIAS_RELU, EK_BIAS_GENERIC, EK_DACT_SOFTPLUS, EK_DACT_RELU, EK_DACT_NONE, EK_TANGENT
+
+USE_CHAIN = True    # fused MLP-chain kernel (k_umma_chain.cu); False = one nero_linear launch per layer
 
 INV_SQRT2 = 0.7071067811865476
 SQRT2 = 1.4142135623730951
@@ -102,16 +105,37 @@ class Predictor:
 
     def forward(self, A, acts, out, m_ptr, m_cap):
         L = self.layers
+        if USE_CHAIN:
+            tail = [CL(L[1], EK_BIAS_RELU, 256, save=Mat(acts[1])), CL(L[2], EK_BIAS_RELU, 256, save=Mat(acts[2])),
+                    CL(L[3], EK_BIAS_GENERIC, self.n_out, save=out, act=self.act, act_param=self.act_param)]
+            if L[0].k_chunks <= 4:
+                chain(A, L[0].k_valid, [CL(L[0], EK_BIAS_RELU, 256, save=Mat(acts[0]))] + tail, m_ptr, m_cap)
+            else:
+                linear(A, L[0], Mat(acts[0]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
+                chain(Mat(acts[0]), 256, tail, m_ptr, m_cap)
+            return
         linear(A, L[0], Mat(acts[0]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
         linear(Mat(acts[0]), L[1], Mat(acts[1]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
         linear(Mat(acts[1]), L[2], Mat(acts[2]), 256, act=ACT_RELU, m_ptr=m_ptr, m_cap=m_cap)
         linear(Mat(acts[2]), L[3], out, self.n_out, act=self.act, act_param=self.act_param, m_ptr=m_ptr, m_cap=m_cap)
 
-    def backward(self, ws, dpre, A, acts, dHa, dHb, m_ptr, m_cap, dX=None, dx_ncol=0, dx_addend=None):
+    def backward(self, ws, dpre, A, acts, dHa, dHb, m_ptr, m_cap, dX=None, dx_ncol=0, dx_addend=None, dHc=None):
         """dpre: Mat over the pre-activation gradient of the output (n_out columns)."""
         L, P = self.layers, self.pl
         g = lambda i: (P[i].weight_v.grad, P[i].weight_g.grad, P[i].bias.grad)
         kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        if USE_CHAIN and dHc is not None:
+            ls = [CL(L[3], EK_DACT_RELU, 256, transposed=True, H=Mat(acts[2]), save=Mat(dHa)),
+                  CL(L[2], EK_DACT_RELU, 256, transposed=True, H=Mat(acts[1]), save=Mat(dHb)),
+                  CL(L[1], EK_DACT_RELU, 256, transposed=True, H=Mat(acts[0]), save=Mat(dHc))]
+            if dX is not None:
+                ls.append(CL(L[0], EK_DACT_NONE, dx_ncol, transposed=True, addend=dx_addend, save=dX))
+            chain(dpre, self.n_out, ls, m_ptr, m_cap)
+            wgrad(ws, dpre, self.n_out, Mat(acts[2]), 256, L[3], *g(3), **kw)
+            wgrad(ws, Mat(dHa), 256, Mat(acts[1]), 256, L[2], *g(2), **kw)
+            wgrad(ws, Mat(dHb), 256, Mat(acts[0]), 256, L[1], *g(1), **kw)
+            wgrad(ws, Mat(dHc), 256, A, L[0].k_valid, L[0], *g(0), **kw)
+            return
         linear(dpre, L[3], Mat(dHa), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(acts[2]), dact=ACT_RELU, **kw)
         wgrad(ws, dpre, self.n_out, Mat(acts[2]), 256, L[3], *g(3), **kw)
         linear(Mat(dHa), L[2], Mat(dHb), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(acts[1]), dact=ACT_RELU, **kw)
@@ -145,10 +169,19 @@ class SdfNet:
         for l in self.L + [self.L8f, self.L8s]:
             l.prep()
 
-    def hidden_forward(self, X0, Hs, H4buf, m_ptr, m_cap):
+    def hidden_forward(self, X0, Hs, H4buf, m_ptr, m_cap, save=True, heads=None):
         """X0 [.,64] -> Hs[k] = input of layer k+1 (k = 0..7); the output of lin3 goes into H4buf[:, :217] scaled by
         1/sqrt2 next to the pre-filled PE/sqrt2 tail (skip concat, field.py:139-140)."""
         kw = dict(act=ACT_SOFTPLUS100, m_ptr=m_ptr, m_cap=m_cap)
+        if USE_CHAIN:
+            sv = (lambda t: Mat(t)) if save else (lambda t: None)
+            ls = [CL(self.L[0], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[0])), CL(self.L[1], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[1])),
+                  CL(self.L[2], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[2])),
+                  CL(self.L[3], EK_BIAS_SOFTPLUS, 217, oscale=INV_SQRT2, save=sv(H4buf), csrc=Mat(H4buf)),
+                  CL(self.L[4], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[4])), CL(self.L[5], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[5])),
+                  CL(self.L[6], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[6])), CL(self.L[7], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[7]))]
+            chain(Mat(X0), self.L[0].k_valid, ls + (heads or []), m_ptr, m_cap)
+            return
         linear(Mat(X0), self.L[0], Mat(Hs[0]), 256, **kw)
         linear(Mat(Hs[0]), self.L[1], Mat(Hs[1]), 256, **kw)
         linear(Mat(Hs[1]), self.L[2], Mat(Hs[2]), 256, **kw)
@@ -161,6 +194,10 @@ class SdfNet:
     def sdf_only(self, X0, SA, SB, SC, out, m_ptr, m_cap):
         """Forward-only SDF value (sampling / occlusion march): hidden stack in 3 rotating buffers, last layer row 0 only."""
         Hs = [SA, SB, SA, SC, SA, SB, SA, SB]
+        if USE_CHAIN:
+            self.hidden_forward(X0, Hs, SC, m_ptr, m_cap, save=False,
+                                heads=[CL(self.L8s, EK_BIAS_GENERIC, 1, save=Mat(out), write_a=False)])
+            return
         self.hidden_forward(X0, Hs, SC, m_ptr, m_cap)
         linear(Mat(SB), self.L8s, Mat(out), 1, m_ptr=m_ptr, m_cap=m_cap)
 
@@ -168,12 +205,28 @@ class SdfNet:
     def forward_with_gradient(self, w, m_ptr, m_cap):
         H = w['H']   # H[1..8]; H[4] has the PE/sqrt2 tail pre-filled by ray_fill
         Hs = [H[1], H[2], H[3], H[4], H[5], H[6], H[7], H[8]]
-        self.hidden_forward(w['X0'], Hs, H[4], m_ptr, m_cap)
         kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        V = w['V']
+        if USE_CHAIN:
+            self.hidden_forward(w['X0'], Hs, H[4], m_ptr, m_cap,
+                                heads=[CL(self.L8f, EK_BIAS_GENERIC, 256, save=Mat(w['Y8']), write_a=False),
+                                       CL(self.L8s, EK_BIAS_GENERIC, 1, save=Mat(w['Y8'], Y8_SDF), write_a=False)])
+            K('nero_dact_times_row', H[8], 256, self.L8s.w_eff, V[7], 256, 256, m_ptr, m_cap)
+            ls = []
+            for k in range(7, 0, -1):
+                if k == 4:
+                    ls.append(CL(self.L[4], EK_DACT_SOFTPLUS, 256, transposed=True, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2,
+                                 ncol_main=217, tail=Mat(w['USKIP']), save=Mat(V[3])))
+                else:
+                    ls.append(CL(self.L[k], EK_DACT_SOFTPLUS, 256, transposed=True, H=Mat(H[k]), save=Mat(V[k - 1])))
+            ls.append(CL(self.L[0], EK_DACT_NONE, 39, transposed=True, save=Mat(w['U0'])))
+            chain(Mat(V[7]), 256, ls, m_ptr, m_cap)
+            K('nero_pe_grad', w['X0'], 64, w['U0'], 64, w['USKIP'], 64, w['G'], m_ptr, m_cap)
+            return
+        self.hidden_forward(w['X0'], Hs, H[4], m_ptr, m_cap)
         linear(Mat(H[8]), self.L8f, Mat(w['Y8']), 256, **kw)                 # feature vector -> Y8[:, 0:256]
         linear(Mat(H[8]), self.L8s, Mat(w['Y8'], Y8_SDF), 1, **kw)          # sdf -> Y8[:, 260]
         # reverse sweep for d sdf / d x  (v_k = sigma_k * u_{k+1}, u_k = W_k^T v_k)
-        V = w['V']
         K('nero_dact_times_row', H[8], 256, self.L8s.w_eff, V[7], 256, 256, m_ptr, m_cap)
         for k in range(7, 0, -1):
             if k == 4:   # u_4 = [217 -> v_3 (through 1/sqrt2) | 39 -> skip branch to the PE input]
@@ -189,36 +242,56 @@ class SdfNet:
         """Given dY8 (feature cols 0..255, sdf col 260) and DG (d loss / d gradient), accumulate all SDF parameter grads."""
         H, V, UB, AB = w['H'], w['V'], w['UB'], w['ABAR']
         kw = dict(m_ptr=m_ptr, m_cap=m_cap)
-        # tangent sweep (adjoint of the reverse sweep): ubar_0 = J_PE dg ; vbar_k = W_k ubar_k ; ubar_{k+1} = sigma_k vbar_k
-        K('nero_pe_tangent', w['X0'], 64, w['DG'], UB[0], 64, UB[4], 256, m_ptr, m_cap)
-        for k in range(8):
-            A = Mat(UB[0]) if k == 0 else Mat(UB[k])
-            if k == 3:
-                linear(A, self.L[3], Mat(UB[4]), 217, use_bias=False, mode=EPI_TANGENT, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2,
-                       dact=ACT_SOFTPLUS100, V=Mat(V[3]), out2=Mat(AB[3]), **kw)
-            else:
-                linear(A, self.L[k], Mat(UB[k + 1]), 256, use_bias=False, mode=EPI_TANGENT, H=Mat(H[k + 1]), dact=ACT_SOFTPLUS100,
-                       V=Mat(V[k]), out2=Mat(AB[k]), **kw)
-        # value backward: abar_7 = sigma_7 * (W8^T ybar) + q_7 ; abar_{k-1} = sigma_{k-1} * (W_k^T abar_k) + q_{k-1}
         dY8 = w['dY8']
-        linear(Mat(dY8), self.L8f, Mat(AB[7]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[8]), dact=ACT_SOFTPLUS100,
-               addend=Mat(AB[7]), **kw)
-        linear(Mat(dY8, Y8_SDF), self.L8s, Mat(AB[7]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[8]), dact=ACT_SOFTPLUS100,
-               addend=Mat(AB[7]), **kw)
-        for k in range(7, 0, -1):
-            if k == 4:
-                linear(Mat(AB[4]), self.L[4], Mat(AB[3]), 217, transposed=True, mode=EPI_MUL_DACT, oscale=INV_SQRT2, H=Mat(H[4]),
-                       hscale=SQRT2, dact=ACT_SOFTPLUS100, addend=Mat(AB[3]), **kw)
-            else:
-                linear(Mat(AB[k]), self.L[k], Mat(AB[k - 1]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[k]),
-                       dact=ACT_SOFTPLUS100, addend=Mat(AB[k - 1]), **kw)
+        # tangent sweep (adjoint of the reverse sweep): ubar_0 = J_PE dg ; vbar_k = W_k ubar_k ; ubar_{k+1} = sigma_k vbar_k,
+        # which also leaves the softplus'' term q_k = 100 (1 - sigma_k) v_k vbar_k in ABAR[k]
+        K('nero_pe_tangent', w['X0'], 64, w['DG'], UB[0], 64, UB[4], 256, m_ptr, m_cap)
+        if USE_CHAIN:
+            ls = []
+            for k in range(8):
+                if k == 3:
+                    ls.append(CL(self.L[3], EK_TANGENT, 217, use_bias=False, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2, V=Mat(V[3]),
+                                 out2=Mat(AB[3]), save=Mat(UB[4]), csrc=Mat(UB[4])))
+                else:
+                    ls.append(CL(self.L[k], EK_TANGENT, 256, use_bias=False, H=Mat(H[k + 1]), V=Mat(V[k]), out2=Mat(AB[k]), save=Mat(UB[k + 1])))
+            chain(Mat(UB[0]), self.L[0].k_valid, ls, m_ptr, m_cap)
+            # value backward: abar_7 = sigma_7*(W8f^T dfeat) + q_7 + dsdf*v_7 (v_7 = sigma_7*W8[0,:] from the reverse sweep);
+            # abar_{k-1} = sigma_{k-1} * (W_k^T abar_k) + q_{k-1}
+            K('nero_row_axpy', Mat(dY8, Y8_SDF), Y8_LD, V[7], 256, AB[7], 256, 256, m_ptr, m_cap)
+            ls = [CL(self.L8f, EK_DACT_SOFTPLUS, 256, transposed=True, H=Mat(H[8]), addend=Mat(AB[7]), save=Mat(AB[7]))]
+            for k in range(7, 0, -1):
+                if k == 4:
+                    ls.append(CL(self.L[4], EK_DACT_SOFTPLUS, 217, transposed=True, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2,
+                                 addend=Mat(AB[3]), save=Mat(AB[3])))
+                else:
+                    ls.append(CL(self.L[k], EK_DACT_SOFTPLUS, 256, transposed=True, H=Mat(H[k]), addend=Mat(AB[k - 1]), save=Mat(AB[k - 1])))
+            chain(Mat(dY8), 256, ls, m_ptr, m_cap)
+        else:
+            for k in range(8):
+                A = Mat(UB[k])
+                if k == 3:
+                    linear(A, self.L[3], Mat(UB[4]), 217, use_bias=False, mode=EPI_TANGENT, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2,
+                           dact=ACT_SOFTPLUS100, V=Mat(V[3]), out2=Mat(AB[3]), **kw)
+                else:
+                    linear(A, self.L[k], Mat(UB[k + 1]), 256, use_bias=False, mode=EPI_TANGENT, H=Mat(H[k + 1]), dact=ACT_SOFTPLUS100,
+                           V=Mat(V[k]), out2=Mat(AB[k]), **kw)
+            linear(Mat(dY8), self.L8f, Mat(AB[7]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[8]), dact=ACT_SOFTPLUS100,
+                   addend=Mat(AB[7]), **kw)
+            linear(Mat(dY8, Y8_SDF), self.L8s, Mat(AB[7]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[8]), dact=ACT_SOFTPLUS100,
+                   addend=Mat(AB[7]), **kw)
+            for k in range(7, 0, -1):
+                if k == 4:
+                    linear(Mat(AB[4]), self.L[4], Mat(AB[3]), 217, transposed=True, mode=EPI_MUL_DACT, oscale=INV_SQRT2, H=Mat(H[4]),
+                           hscale=SQRT2, dact=ACT_SOFTPLUS100, addend=Mat(AB[3]), **kw)
+                else:
+                    linear(Mat(AB[k]), self.L[k], Mat(AB[k - 1]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[k]),
+                           dact=ACT_SOFTPLUS100, addend=Mat(AB[k - 1]), **kw)
         # weight gradients: dW_k = abar_k^T h_k + v_k^T ubar_k
         ls = self.sp.layers()
         for k in range(8):
             Hin = Mat(w['X0']) if k == 0 else Mat(H[k])
-            Uin = Mat(UB[0]) if k == 0 else Mat(UB[k])
             wgrad(ws, Mat(AB[k]), self.nout[k], Hin, self.L[k].k_valid, self.L[k], ls[k].weight_v.grad, ls[k].weight_g.grad,
-                  ls[k].bias.grad, dY2=Mat(V[k]), X2=Uin, **kw)
+                  ls[k].bias.grad, dY2=Mat(V[k]), X2=Mat(UB[k]), **kw)
         l8 = ls[8]
         wgrad(ws, Mat(dY8), 256, Mat(H[8]), 256, self.L8f, l8.weight_v.grad, l8.weight_g.grad, l8.bias.grad, **kw)
         # sdf row: dW8[0,:] = sum_m dsdf[m] h8[m,:] + sum_m ubar_8[m,:] ; db8[0] = sum dsdf
@@ -401,7 +474,7 @@ class ShapeEngine:
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
         w = self.w
         w.update(dALPHA_IN=z(cap), dCOLOR_IN=z(cap, 4), DOUTS=z(cap, O_LDIM), DNOV=z(cap), dE_dir=z(cap, 128), dE_inn=z(cap, 128),
-                 dE_dif=z(cap, 128), dEH=z(cap, 64), DG=z(cap, 4), dY8=z(cap, Y8_LD), dHa=z(cap, 256), dHb=z(cap, 256),
+                 dE_dif=z(cap, 128), dEH=z(cap, 64), DG=z(cap, 4), dY8=z(cap, Y8_LD), dHa=z(cap, 256), dHb=z(cap, 256), dHc=z(cap, 256),
                  D_INV_S=z(1))
         w['UB'] = [z(cap, 64)] + [z(cap, 256) for _ in range(8)]
         w['ABAR'] = [z(cap, 256) for _ in range(8)]
@@ -551,19 +624,19 @@ class ShapeEngine:
         K('nero_shade_combine_bwd', w['OUTS'], w['GEO'], self.lut, self.exp_max, 1 if self.human else 0, w['dCOLOR_IN'], docc, w['DOUTS'],
           w['DNOV'], n_in, cap)
         A = w['ACT']
-        dHa, dHb = w['dHa'], w['dHb']
-        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LDIR), Mat(w['E'], E_IDER), A['odir'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dir']), dx_ncol=72)
-        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LD), Mat(w['E'], E_IDEN), A['odif'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dif']), dx_ncol=72)
-        self.m_inner.backward(ws, Mat(w['DOUTS'], O_LI), Mat(w['E'], E_PE8X), A['inner'], dHa, dHb, n_in, cap, dX=Mat(w['dE_inn']), dx_ncol=72)
-        self.m_iw.backward(ws, Mat(w['DOUTS'], O_IW), Mat(w['E'], 0), A['iw'], dHa, dHb, n_in, cap)
+        dHa, dHb, dHc = w['dHa'], w['dHb'], w['dHc']
+        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LDIR), Mat(w['E'], E_IDER), A['odir'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dir']), dx_ncol=72, dHc=dHc)
+        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LD), Mat(w['E'], E_IDEN), A['odif'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dif']), dx_ncol=72, dHc=dHc)
+        self.m_inner.backward(ws, Mat(w['DOUTS'], O_LI), Mat(w['E'], E_PE8X), A['inner'], dHa, dHb, n_in, cap, dX=Mat(w['dE_inn']), dx_ncol=72, dHc=dHc)
+        self.m_iw.backward(ws, Mat(w['DOUTS'], O_IW), Mat(w['E'], 0), A['iw'], dHa, dHb, n_in, cap, dHc=dHc)
         if self.human:
-            self.m_human.backward(ws, Mat(w['DOUTS'], O_HUM), Mat(w['EH']), A['human'], dHa, dHb, n_in, cap, dX=Mat(w['dEH']), dx_ncol=24)
+            self.m_human.backward(ws, Mat(w['DOUTS'], O_HUM), Mat(w['EH']), A['human'], dHa, dHb, n_in, cap, dX=Mat(w['dEH']), dx_ncol=24, dHc=dHc)
         K('nero_shade_prep_bwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['GEO'], w['dE_dir'], 128, w['dE_inn'], 128, w['dE_dif'], 128,
           w['dEH'] if self.human else None, 64, st['hp'], w['DNOV'], w['DOUTS'], w['DG'], n_in, cap)
         matin = Mat(w['Y8'])
-        self.m_rough.backward(ws, Mat(w['DOUTS'], O_ROUGH), matin, A['rough'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256)
-        self.m_met.backward(ws, Mat(w['DOUTS'], O_MET), matin, A['met'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']))
-        self.m_alb.backward(ws, Mat(w['DOUTS'], O_ALB), matin, A['alb'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']))
+        self.m_rough.backward(ws, Mat(w['DOUTS'], O_ROUGH), matin, A['rough'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dHc=dHc)
+        self.m_met.backward(ws, Mat(w['DOUTS'], O_MET), matin, A['met'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']), dHc=dHc)
+        self.m_alb.backward(ws, Mat(w['DOUTS'], O_ALB), matin, A['alb'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']), dHc=dHc)
         # ---- SDF -> alpha
         w['D_INV_S'].zero_()
         dg = None if d_gerr is None else d_gerr.contiguous()

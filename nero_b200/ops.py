@@ -309,3 +309,117 @@ def K(name, *args):
     rc = getattr(lib, name)(*conv, _stream())
     _check(rc, name)
     launch_count += 1
+
+
+# ------------------------------------------------------------------------------------------------ fused MLP chain
+EK_BIAS_SOFTPLUS, EK_BIAS_RELU, EK_BIAS_GENERIC, EK_DACT_SOFTPLUS, EK_DACT_RELU, EK_DACT_NONE, EK_TANGENT = range(7)
+
+
+class _ChainLayer(ctypes.Structure):
+    _fields_ = [('wimg', ctypes.c_void_p), ('bias', ctypes.c_void_p),
+                ('save', ctypes.c_void_p), ('H', ctypes.c_void_p), ('addend', ctypes.c_void_p), ('V', ctypes.c_void_p),
+                ('out2', ctypes.c_void_p), ('tail', ctypes.c_void_p),
+                ('n_pad', ctypes.c_int), ('k_chunks', ctypes.c_int), ('n_bias', ctypes.c_int), ('ncol_out', ctypes.c_int),
+                ('ncol_main', ctypes.c_int), ('kind', ctypes.c_int), ('act', ctypes.c_int),
+                ('ld_save', ctypes.c_int), ('ldh', ctypes.c_int), ('ldadd', ctypes.c_int), ('ldv', ctypes.c_int),
+                ('ldo2', ctypes.c_int), ('ldt', ctypes.c_int),
+                ('oscale', ctypes.c_float), ('hscale', ctypes.c_float), ('act_param', ctypes.c_float),
+                ('write_a', ctypes.c_int), ('a_blocks', ctypes.c_int),
+                ('csrc', ctypes.c_void_p), ('ld_csrc', ctypes.c_int), ('pad_', ctypes.c_int)]
+
+
+class _ChainParams(ctypes.Structure):
+    _fields_ = [('A0', ctypes.c_void_p), ('lda0', ctypes.c_int), ('k_valid0', ctypes.c_int),
+                ('n_layers', ctypes.c_int), ('m_ptr', ctypes.c_void_p), ('m_cap', ctypes.c_int),
+                ('L', _ChainLayer * 10)]
+
+
+def _p(m):
+    if m is None:
+        return None
+    if isinstance(m, Mat):
+        return m.t.data_ptr() + 4 * m.c0
+    return m.data_ptr()
+
+
+def chain_layer(layer: PreparedLayer, kind, ncol_out, *, transposed=False, save: Mat = None, act=ACT_NONE, act_param=0.0, oscale=1.0,
+                H: Mat = None, hscale=1.0, V: Mat = None, out2: Mat = None, addend: Mat = None, ncol_main=None, tail: Mat = None,
+                write_a=True, csrc: Mat = None, use_bias=True):
+    """Describe one layer of a fused chain (same semantics as ops.linear for the matching kind)."""
+    return dict(layer=layer, kind=kind, ncol_out=ncol_out, transposed=transposed, save=save, act=act, act_param=act_param, oscale=oscale,
+                H=H, hscale=hscale, V=V, out2=out2, addend=addend, ncol_main=ncol_out if ncol_main is None else ncol_main, tail=tail,
+                write_a=write_a, csrc=csrc, use_bias=use_bias)
+
+
+def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None):
+    """Run consecutive layers on each 128-row tile with the A operand kept in TMEM (k_umma_chain.cu)."""
+    global launch_count
+    assert 1 <= len(layers) <= 10
+    if m_cap is None:
+        m_cap = A0.t.shape[0]
+    if DEBUG_GEMM == 'torch':
+        return _chain_unfused(A0, k_valid0, layers, m_ptr, m_cap)
+    P = _ChainParams()
+    P.A0, P.lda0, P.k_valid0 = _p(A0), A0.ld, ceil_div(k_valid0, 4) * 4
+    P.n_layers, P.m_ptr, P.m_cap = len(layers), _p(m_ptr), m_cap
+    keep = []
+    for i, d in enumerate(layers):
+        lay, L = d['layer'], P.L[i]
+        if d['transposed']:
+            img, n_pad, k_chunks, bias = lay.img_t, lay.t_npad, lay.t_chunks, None
+        else:
+            img, n_pad, k_chunks = lay.img_f, lay.n_pad, lay.k_chunks
+            bias = lay.bias_view() if d['use_bias'] else None
+        assert k_chunks <= 4 and d['ncol_out'] <= n_pad
+        keep.append(bias)
+        L.wimg, L.bias, L.n_bias = _p(img), _p(bias), 0 if bias is None else bias.numel()
+        L.n_pad, L.k_chunks, L.ncol_out, L.ncol_main, L.kind, L.act = n_pad, k_chunks, d['ncol_out'], d['ncol_main'], d['kind'], d['act']
+        for name, key, ldname in (('save', 'save', 'ld_save'), ('H', 'H', 'ldh'), ('addend', 'addend', 'ldadd'), ('V', 'V', 'ldv'),
+                                  ('out2', 'out2', 'ldo2'), ('tail', 'tail', 'ldt'), ('csrc', 'csrc', 'ld_csrc')):
+            m = d[key]
+            setattr(L, name, _p(m))
+            setattr(L, ldname, m.ld if m is not None else 0)
+        L.oscale, L.hscale, L.act_param = d['oscale'], d['hscale'], d['act_param']
+        L.write_a = 1 if (d['write_a'] and i + 1 < len(layers)) else 0
+        nxt = layers[i + 1]['layer'] if i + 1 < len(layers) else None
+        if nxt is not None:
+            nk = nxt.t_chunks if layers[i + 1]['transposed'] else nxt.k_chunks
+            L.a_blocks = 4 * nk
+        if DRY_RUN:
+            assert img is not None
+            if d['kind'] in (EK_DACT_SOFTPLUS, EK_DACT_RELU, EK_TANGENT):
+                assert d['H'] is not None
+            if d['kind'] == EK_TANGENT:
+                assert d['V'] is not None and d['out2'] is not None
+    if DRY_RUN:
+        assert A0.c0 % 4 == 0 and A0.ld % 4 == 0 and A0.c0 + P.k_valid0 <= A0.t.shape[1]
+        return
+    rc = lib.nero_chain(ctypes.byref(P), _stream())
+    _check(rc, 'nero_chain')
+    launch_count += 1
+
+
+def _chain_unfused(A0, k_valid0, layers, m_ptr, m_cap):
+    """Debug emulation: the same chain as separate (emulated) linear calls through a scratch buffer."""
+    dev = A0.t.device
+    cur = Mat(torch.zeros(m_cap, 256, device=dev))
+    M = _m_of(m_ptr, m_cap)
+    cur.t[:M, :k_valid0] = A0.t[:M, A0.c0:A0.c0 + k_valid0]
+    kind2mode = {EK_BIAS_SOFTPLUS: (EPI_BIAS_ACT, ACT_SOFTPLUS100, ACT_NONE), EK_BIAS_RELU: (EPI_BIAS_ACT, ACT_RELU, ACT_NONE),
+                 EK_BIAS_GENERIC: (EPI_BIAS_ACT, None, ACT_NONE), EK_DACT_SOFTPLUS: (EPI_MUL_DACT, ACT_NONE, ACT_SOFTPLUS100),
+                 EK_DACT_RELU: (EPI_MUL_DACT, ACT_NONE, ACT_RELU), EK_DACT_NONE: (EPI_MUL_DACT, ACT_NONE, ACT_NONE),
+                 EK_TANGENT: (EPI_TANGENT, ACT_NONE, ACT_SOFTPLUS100)}
+    for i, d in enumerate(layers):
+        mode, act, dact = kind2mode[d['kind']]
+        act = d['act'] if act is None else act
+        out = d['save'] if d['save'] is not None else Mat(torch.zeros(m_cap, 256, device=dev))
+        linear(cur, d['layer'], out, d['ncol_out'], transposed=d['transposed'], mode=mode, act=act, act_param=d['act_param'],
+               oscale=d['oscale'], H=d['H'], hscale=d['hscale'], dact=dact, V=d['V'], out2=d['out2'], addend=d['addend'],
+               ncol_main=d['ncol_main'], tail=d['tail'], m_ptr=m_ptr, m_cap=m_cap, use_bias=d['use_bias'])
+        if d['write_a'] and i + 1 < len(layers):
+            nm = d['ncol_out'] if mode == EPI_BIAS_ACT else min(d['ncol_out'], d['ncol_main'])
+            nxt = torch.zeros(m_cap, 256, device=dev)
+            nxt[:M, :nm] = out.t[:M, out.c0:out.c0 + nm]
+            if d['csrc'] is not None:
+                nxt[:M, nm:256] = d['csrc'].t[:M, d['csrc'].c0 + nm:d['csrc'].c0 + 256]
+            cur = Mat(nxt)
