@@ -104,6 +104,12 @@ int nero_ray_fill(const float* rays_o, const float* rays_d, const float* z_vals,
                   int* slot, float* pts, int* ray_in, float* X0, int ld_x0, float* Y8, int ld_y8, float* H4, int ld_h4,
                   float* XN, int ld_xn, float* H5, int ld_h5, float* FV, int ld_fv, float* dist_out, int* ray_out, void* stream);
 
+/* init-sdf regulariser points (network/renderer.py:591-594): ordered compaction of samples with |p| < radius + PE rows */
+int nero_reg_prepare(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, int* cnt, int* cnt_dummy,
+                     int* off, int* off_dummy, int* n, int* n_dummy, void* stream);
+int nero_reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
+                  float* X0, int ldx, float* H4, int ldh, void* stream);
+
 /* ---- analytic SDF gradient helpers (SDFNetwork.gradient, network/field.py:155-167) ------------------------- */
 int nero_dact_times_row(const float* H, int ldh, const float* row, float* V, int ldv, int ncol, const int* m_ptr, int m_cap, void* stream);
 int nero_pe_grad(const float* X0, int ldx, const float* U0, int ldu, const float* US, int lds, float* G, const int* m_ptr, int m_cap, void* stream);

@@ -117,6 +117,10 @@ int occ_init(const float* pts, const float* refl, const int* sel, const int* p_p
 int occ_select(const float* pts, const float* Y8, int ldy, int sdf_col, const float* G, const int* ray_in, const float* rays_d,
                float sdf_thresh, const int* m_ptr, int m_cap, int* sel, int* count, cudaStream_t st);
 int row_axpy(const float* a, int lda, const float* X, int ldx, float* Y, int ldy, int ncol, const int* m_ptr, int m_cap, cudaStream_t st);
+int reg_prepare(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, int* cnt, int* cnt_dummy,
+                int* off, int* off_dummy, int* n, int* n_dummy, cudaStream_t st);
+int reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
+             float* X0, int ldx, float* H4, int ldh, cudaStream_t st);
 struct ChainParams;
 int chain_dispatch(const ChainParams& p, cudaStream_t stream);
 int occ_loss(const float* occ_prob, const float* gt, const int* sel, const int* p_ptr, int p_cap, float* loss_sum, float* docc_sign,
@@ -174,6 +178,14 @@ int nero_set_ide_table(const float* mat17x36_host) { return set_ide_table(mat17x
 int nero_chain(const void* chain_params_host, void* stream) {
   if (!chain_params_host) return NERO_ERR_ARG;
   return chain_dispatch(*reinterpret_cast<const ChainParams*>(chain_params_host), (cudaStream_t)stream);
+}
+int nero_reg_prepare(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, int* cnt, int* cnt_dummy,
+                     int* off, int* off_dummy, int* n, int* n_dummy, void* stream) {
+  return reg_prepare(rays_o, rays_d, z_vals, R, S, radius, cnt, cnt_dummy, off, off_dummy, n, n_dummy, (cudaStream_t)stream);
+}
+int nero_reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
+                  float* X0, int ldx, float* H4, int ldh, void* stream) {
+  return reg_fill(rays_o, rays_d, z_vals, R, S, radius, off, pts, X0, ldx, H4, ldh, (cudaStream_t)stream);
 }
 int nero_row_axpy(const float* a, int lda, const float* X, int ldx, float* Y, int ldy, int ncol, const int* m_ptr, int m_cap, void* stream) {
   return row_axpy(a, lda, X, ldx, Y, ldy, ncol, m_ptr, m_cap, (cudaStream_t)stream);

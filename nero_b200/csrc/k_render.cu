@@ -12,6 +12,7 @@
 namespace nero {
 
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
+static inline int blocks_for(long n, int per) { return int((n + per - 1) / per); }
 
 __device__ __forceinline__ int load_count(const int* p, int cap) {
   int m = p ? *p : cap;
@@ -145,6 +146,57 @@ __global__ void ray_fill_kernel(const FillParams q) {
     }
     base_in += __popc(bi);
     base_out += __popc(bo);
+  }
+}
+
+// ------------------------------------------------------------------ init-sdf regulariser points (renderer.py:591-594)
+// mask = |mid-point| < radius over ALL samples; ordered compaction of the points + PE rows for a value-only SDF pass
+__global__ void reg_classify_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                    const float* __restrict__ z_vals, int R, int S, float radius, int* cnt) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float o[3] = {rays_o[r * 3], rays_o[r * 3 + 1], rays_o[r * 3 + 2]};
+  const float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+  int n = 0;
+  for (int j0 = 0; j0 < S; j0 += 32) {
+    const int j = j0 + lane;
+    bool in = false;
+    if (j < S) {
+      float p[3], dist;
+      sample_point(z_vals + size_t(r) * S, S, j, o, d, p, &dist);
+      in = norm3_rn(p) < radius;
+    }
+    n += __popc(__ballot_sync(0xffffffffu, in));
+  }
+  if (lane == 0) cnt[r] = n;
+}
+__global__ void reg_fill_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                                int R, int S, float radius, const int* __restrict__ off, float* pts, float* X0, int ldx, float* H4,
+                                int ldh) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float o[3] = {rays_o[r * 3], rays_o[r * 3 + 1], rays_o[r * 3 + 2]};
+  const float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+  int base = off[r];
+  for (int j0 = 0; j0 < S; j0 += 32) {
+    const int j = j0 + lane;
+    bool in = false;
+    float p[3] = {0, 0, 0}, dist = 0.f;
+    if (j < S) {
+      sample_point(z_vals + size_t(r) * S, S, j, o, d, p, &dist);
+      in = norm3_rn(p) < radius;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int i = base + __popc(b & ((1u << lane) - 1u));
+      *reinterpret_cast<float4*>(pts + size_t(i) * 4) = make_float4(p[0], p[1], p[2], dist);
+      float pe[39];
+      pe_encode<3>(p, 6, pe);
+      for (int c = 0; c < 39; ++c) { X0[size_t(i) * ldx + c] = pe[c]; H4[size_t(i) * ldh + 217 + c] = pe[c] * kInvSqrt2; }
+    }
+    base += __popc(b);
   }
 }
 
@@ -346,13 +398,27 @@ __global__ void composite_kernel(const int* __restrict__ slot, int R, int S, con
 }
 
 // ------------------------------------------------------------------ host launchers
-static inline int blocks_for(long n, int per) { return int((n + per - 1) / per); }
 
 int ray_prepare(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, int* cnt_in, int* cnt_out,
                 int* off_in, int* off_out, int* n_in, int* n_out, cudaStream_t st) {
   if (R <= 0) return NERO_OK;
   ray_classify_kernel<<<blocks_for(long(R) * 32, 256), 256, 0, st>>>(rays_o, rays_d, z_vals, R, S, cnt_in, cnt_out);
   ray_scan_kernel<<<1, 1024, 0, st>>>(cnt_in, cnt_out, R, off_in, off_out, n_in, n_out);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+int reg_prepare(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, int* cnt, int* cnt_dummy,
+                int* off, int* off_dummy, int* n, int* n_dummy, cudaStream_t st) {
+  if (R <= 0) return NERO_OK;
+  reg_classify_kernel<<<blocks_for(long(R) * 32, 256), 256, 0, st>>>(rays_o, rays_d, z_vals, R, S, radius, cnt);
+  ray_scan_kernel<<<1, 1024, 0, st>>>(cnt, cnt_dummy, R, off, off_dummy, n, n_dummy);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+int reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
+             float* X0, int ldx, float* H4, int ldh, cudaStream_t st) {
+  if (R <= 0) return NERO_OK;
+  reg_fill_kernel<<<blocks_for(long(R) * 32, 128), 128, 0, st>>>(rays_o, rays_d, z_vals, R, S, radius, off, pts, X0, ldx, H4, ldh);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

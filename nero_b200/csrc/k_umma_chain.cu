@@ -47,7 +47,8 @@ constexpr int kChThreads = (kChEpiWarps + 2) * 32;
 constexpr int kChStages = 3;
 constexpr uint32_t kChStageBytes = 2 * 256 * 128;                       // W chunk: hi + lo planes of up to 256 rows
 constexpr uint32_t kChEpiBytes = kChEpiWarps * kStageWarpBytes;         // 30 KB
-constexpr uint32_t kChSmemBytes = kChStages * kChStageBytes + kChEpiBytes + 1024 + 256;
+constexpr uint32_t kChBiasBytes = 2 * 256 * 4;
+constexpr uint32_t kChSmemBytes = kChStages * kChStageBytes + kChEpiBytes + kChBiasBytes + 1024 + 256;
 constexpr uint32_t kAccCol = 0, kAHiCol = 256, kALoCol = 384;
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
@@ -78,7 +79,7 @@ __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const
 
 template <int KIND>
 __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32_t tmem_lane_base, int row0, int rows_valid,
-                                                     int third, int lane, float* stg) {
+                                                     int third, int lane, float* stg, const float* s_bias) {
   constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
   const int nblk = L.n_pad >> 4;
   const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
@@ -97,8 +98,7 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
       if constexpr (kBias) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          const float x = v[j] + ((L.bias && col < L.n_bias) ? __ldg(L.bias + col) : 0.0f);
+          const float x = v[j] + s_bias[c0 + j];
           float y;
           if constexpr (KIND == EK_BIAS_SOFTPLUS) y = softplus100_fast(x);
           else if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(x, 0.0f);
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_epi = reinterpret_cast<float*>(smem + kChStages * kChStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChStages * kChStageBytes + kChEpiBytes);
+  float* s_bias2 = reinterpret_cast<float*>(smem + kChStages * kChStageBytes + kChEpiBytes);   // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChStages * kChStageBytes + kChEpiBytes + kChBiasBytes);
   uint64_t* full = bars;                        // [stages]  W chunk landed
   uint64_t* empty = bars + kChStages;           // [stages]  W chunk consumed
   uint64_t* a_ready = bars + 2 * kChStages;     // A operand written + accumulator drained (12 epilogue warps)
@@ -224,17 +225,25 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           prefetch_rows_l2(L.addend ? L.addend + size_t(row0) * L.ldadd : nullptr, L.ldadd, rows_valid, nm, lane);
           if (L.kind == EK_TANGENT) prefetch_rows_l2(L.V + size_t(row0) * L.ldv, L.ldv, rows_valid, nm, lane);
         }
+        // bias of this layer -> smem buffer (l & 1): written while the MMAs run; the named barrier below orders it
+        // against the reads (two buffers + one barrier per layer make the reuse race-free)
+        float* sb = s_bias2 + (l & 1) * 256;
+        if (warp < 8) {
+          const int i = warp * 32 + lane;
+          sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
+        }
         mbar_wait(acc_ready, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after();
+        asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
         switch (L.kind) {
-          case EK_BIAS_SOFTPLUS: chain_epilogue_layer<EK_BIAS_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg); break;
-          case EK_BIAS_RELU: chain_epilogue_layer<EK_BIAS_RELU>(L, tl, row0, rows_valid, third, lane, stg); break;
-          case EK_BIAS_GENERIC: chain_epilogue_layer<EK_BIAS_GENERIC>(L, tl, row0, rows_valid, third, lane, stg); break;
-          case EK_DACT_SOFTPLUS: chain_epilogue_layer<EK_DACT_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg); break;
-          case EK_DACT_RELU: chain_epilogue_layer<EK_DACT_RELU>(L, tl, row0, rows_valid, third, lane, stg); break;
-          case EK_DACT_NONE: chain_epilogue_layer<EK_DACT_NONE>(L, tl, row0, rows_valid, third, lane, stg); break;
-          default: chain_epilogue_layer<EK_TANGENT>(L, tl, row0, rows_valid, third, lane, stg); break;
+          case EK_BIAS_SOFTPLUS: chain_epilogue_layer<EK_BIAS_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+          case EK_BIAS_RELU: chain_epilogue_layer<EK_BIAS_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+          case EK_BIAS_GENERIC: chain_epilogue_layer<EK_BIAS_GENERIC>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+          case EK_DACT_SOFTPLUS: chain_epilogue_layer<EK_DACT_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+          case EK_DACT_RELU: chain_epilogue_layer<EK_DACT_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+          case EK_DACT_NONE: chain_epilogue_layer<EK_DACT_NONE>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+          default: chain_epilogue_layer<EK_TANGENT>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
         }
         tmem_st_wait();
         tcgen05_fence_before();

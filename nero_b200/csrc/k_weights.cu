@@ -17,12 +17,13 @@ namespace nero {
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int w = tid >> 5, l = tid & 31;
   __syncthreads();
   if (l == 0) sh[w] = v;
   __syncthreads();
   float t = 0.0f;
-  for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+  for (int i = 0; i < ((blockDim.x * blockDim.y) >> 5); ++i) t += sh[i];
   return t;
 }
 
@@ -70,33 +71,39 @@ int prep_weight(const float* v, const float* g, int K, int row0, int nrows, cons
   return NERO_OK;
 }
 
-// one block per layer row n = row0 + blockIdx.x
+// one block per layer row n = row0 + blockIdx.x; blockDim = (kcols, 4): the P split-K partials are summed by 4 thread
+// groups in parallel (the per-row reads are latency bound), then reduced through shared memory.
 __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
                                     const float* __restrict__ bias_partial, int K, int row0,
                                     const int* __restrict__ kmap, float in_scale, const float* __restrict__ v,
                                     const float* __restrict__ g, float* grad_w, float* grad_g, float* grad_b,
                                     const float* __restrict__ extra_row, float extra_scale) {
   __shared__ float sh[32];
-  extern __shared__ float s_dw[];  // [K]
+  extern __shared__ float s_dw[];  // [4][K] partial sums, then [K] in slot 0
   const int r = blockIdx.x, n = row0 + r;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+  const size_t pstride = size_t(rows_partial) * ld_partial;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const int kc = kmap ? kmap[k] : k;
     const float* pp = partial + size_t(r) * ld_partial + kc;
-    const size_t pstride = size_t(rows_partial) * ld_partial;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int pidx = 0;
-    for (; pidx + 3 < P; pidx += 4) {   // 4 independent partial sums: the loads of one row are latency bound
-      a0 += pp[size_t(pidx) * pstride]; a1 += pp[size_t(pidx + 1) * pstride];
-      a2 += pp[size_t(pidx + 2) * pstride]; a3 += pp[size_t(pidx + 3) * pstride];
+    int pidx = threadIdx.y;
+    for (; pidx + 12 < P; pidx += 16) {
+      a0 += pp[size_t(pidx) * pstride]; a1 += pp[size_t(pidx + 4) * pstride];
+      a2 += pp[size_t(pidx + 8) * pstride]; a3 += pp[size_t(pidx + 12) * pstride];
     }
-    for (; pidx < P; ++pidx) a0 += pp[size_t(pidx) * pstride];
-    float acc = (a0 + a1) + (a2 + a3);
-    acc *= in_scale;
-    if (extra_row && r == 0) acc += extra_scale * extra_row[kc];
-    s_dw[k] = acc;
+    for (; pidx < P; pidx += 4) a0 += pp[size_t(pidx) * pstride];
+    s_dw[threadIdx.y * K + k] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  if (grad_b && bias_partial && threadIdx.x == 0) {
+  for (int k = tid; k < K; k += nthreads) {
+    const int kc = kmap ? kmap[k] : k;
+    float acc = ((s_dw[k] + s_dw[K + k]) + (s_dw[2 * K + k] + s_dw[3 * K + k])) * in_scale;
+    if (extra_row && r == 0) acc += extra_scale * extra_row[kc];
+    s_dw[k] = acc;   // slot 0 (each k is read and written by the same thread)
+  }
+  __syncthreads();
+  if (grad_b && bias_partial && tid == 0) {
     float b = 0.0f;
     for (int pidx = 0; pidx < P; ++pidx) b += bias_partial[size_t(pidx) * rows_partial + r];
     grad_b[n] += b;
@@ -104,17 +111,17 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, in
   if (g) {
     const float* vr = v + size_t(n) * K;
     float ss = 0.0f, dot = 0.0f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) { ss += vr[k] * vr[k]; dot += s_dw[k] * vr[k]; }
+    for (int k = tid; k < K; k += nthreads) { ss += vr[k] * vr[k]; dot += s_dw[k] * vr[k]; }
     ss = block_sum(ss, sh);
     dot = block_sum(dot, sh);
     const float inv_norm = rsqrtf(ss);
     const float dg = dot * inv_norm;                 // dL/dg = dW . v_hat
     const float c = g[n] * inv_norm;
-    for (int k = threadIdx.x; k < K; k += blockDim.x)
+    for (int k = tid; k < K; k += nthreads)
       grad_w[size_t(n) * K + k] += c * (s_dw[k] - dg * vr[k] * inv_norm);
-    if (threadIdx.x == 0) grad_g[n] += dg;
+    if (tid == 0) grad_g[n] += dg;
   } else {
-    for (int k = threadIdx.x; k < K; k += blockDim.x) grad_w[size_t(n) * K + k] += s_dw[k];
+    for (int k = tid; k < K; k += nthreads) grad_w[size_t(n) * K + k] += s_dw[k];
   }
 }
 
@@ -122,9 +129,11 @@ int wgrad_finish(const float* partial, int P, int rows_partial, int ld_partial, 
                  int row0, int nrows, const int* kmap, float in_scale, const float* v, const float* g, float* grad_w,
                  float* grad_g, float* grad_b, const float* extra_row, float extra_scale, cudaStream_t stream) {
   if (nrows <= 0) return NERO_OK;
-  wgrad_finish_kernel<<<nrows, 256, K * sizeof(float), stream>>>(partial, P, rows_partial, ld_partial, bias_partial, K, row0,
-                                                                 kmap, in_scale, v, g, grad_w, grad_g, grad_b, extra_row,
-                                                                 extra_scale);
+  int bx = 32;
+  while (bx < K && bx < 256) bx <<= 1;
+  wgrad_finish_kernel<<<nrows, dim3(bx, 4), 4 * K * sizeof(float), stream>>>(partial, P, rows_partial, ld_partial, bias_partial, K, row0,
+                                                                            kmap, in_scale, v, g, grad_w, grad_g, grad_b, extra_row,
+                                                                            extra_scale);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

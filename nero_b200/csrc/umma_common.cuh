@@ -46,23 +46,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // coalesced load of a [32 rows x 16 cols] block (row-major global, leading dim ld) into registers of the
 // "lane = row" layout, through the warp's transpose buffer.  Rows >= rows_valid / cols >= cols_valid read as 0.
+// Full, 16-byte aligned blocks take a branch-free fast path (4 LDG.128 + 4 STS.128 + 4 LDS.128).
 __device__ __forceinline__ void load_block16(const float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec,
                                              float* stage, int lane, float* r) {
+  float* sdst = stage + (lane >> 2) * kStagePitch + (lane & 3) * 4;
+  if (vec && rows_valid >= 32 && cols_valid >= 16) {
+    const float* src = g + size_t(lane >> 2) * ld + (lane & 3) * 4;
+    const size_t ld8 = size_t(ld) * 8;
+    float4 x0 = *reinterpret_cast<const float4*>(src);
+    float4 x1 = *reinterpret_cast<const float4*>(src + ld8);
+    float4 x2 = *reinterpret_cast<const float4*>(src + 2 * ld8);
+    float4 x3 = *reinterpret_cast<const float4*>(src + 3 * ld8);
+    *reinterpret_cast<float4*>(sdst) = x0;
+    *reinterpret_cast<float4*>(sdst + 8 * kStagePitch) = x1;
+    *reinterpret_cast<float4*>(sdst + 16 * kStagePitch) = x2;
+    *reinterpret_cast<float4*>(sdst + 24 * kStagePitch) = x3;
+  } else {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows_valid) {
-      const float* p = g + size_t(row) * ld + q;
-      if (vec && q + 3 < cols_valid) x = *reinterpret_cast<const float4*>(p);
-      else {
-        if (q < cols_valid) x.x = p[0];
-        if (q + 1 < cols_valid) x.y = p[1];
-        if (q + 2 < cols_valid) x.z = p[2];
-        if (q + 3 < cols_valid) x.w = p[3];
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows_valid) {
+        const float* p = g + size_t(row) * ld + q;
+        if (vec && q + 3 < cols_valid) x = *reinterpret_cast<const float4*>(p);
+        else {
+          if (q < cols_valid) x.x = p[0];
+          if (q + 1 < cols_valid) x.y = p[1];
+          if (q + 2 < cols_valid) x.z = p[2];
+          if (q + 3 < cols_valid) x.w = p[3];
+        }
       }
+      *reinterpret_cast<float4*>(stage + row * kStagePitch + q) = x;
     }
-    *reinterpret_cast<float4*>(stage + row * kStagePitch + q) = x;
   }
   __syncwarp();
 #pragma unroll
@@ -79,18 +94,32 @@ __device__ __forceinline__ void store_block16(float* __restrict__ g, int ld, int
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<float4*>(stage + lane * kStagePitch + j * 4) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
   __syncwarp();
+  if (vec && rows_valid >= 32 && cols_valid >= 16) {
+    const float* ssrc = stage + (lane >> 2) * kStagePitch + (lane & 3) * 4;
+    float* dst = g + size_t(lane >> 2) * ld + (lane & 3) * 4;
+    const size_t ld8 = size_t(ld) * 8;
+    const float4 x0 = *reinterpret_cast<const float4*>(ssrc);
+    const float4 x1 = *reinterpret_cast<const float4*>(ssrc + 8 * kStagePitch);
+    const float4 x2 = *reinterpret_cast<const float4*>(ssrc + 16 * kStagePitch);
+    const float4 x3 = *reinterpret_cast<const float4*>(ssrc + 24 * kStagePitch);
+    *reinterpret_cast<float4*>(dst) = x0;
+    *reinterpret_cast<float4*>(dst + ld8) = x1;
+    *reinterpret_cast<float4*>(dst + 2 * ld8) = x2;
+    *reinterpret_cast<float4*>(dst + 3 * ld8) = x3;
+  } else {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
-    if (row < rows_valid && q < cols_valid) {
-      const float4 x = *reinterpret_cast<const float4*>(stage + row * kStagePitch + q);
-      float* p = g + size_t(row) * ld + q;
-      if (vec && q + 3 < cols_valid) *reinterpret_cast<float4*>(p) = x;
-      else {
-        p[0] = x.x;
-        if (q + 1 < cols_valid) p[1] = x.y;
-        if (q + 2 < cols_valid) p[2] = x.z;
-        if (q + 3 < cols_valid) p[3] = x.w;
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+      if (row < rows_valid && q < cols_valid) {
+        const float4 x = *reinterpret_cast<const float4*>(stage + row * kStagePitch + q);
+        float* p = g + size_t(row) * ld + q;
+        if (vec && q + 3 < cols_valid) *reinterpret_cast<float4*>(p) = x;
+        else {
+          p[0] = x.x;
+          if (q + 1 < cols_valid) p[1] = x.y;
+          if (q + 2 < cols_valid) p[2] = x.z;
+          if (q + 3 < cols_valid) p[3] = x.w;
+        }
       }
     }
   }

@@ -303,9 +303,50 @@ class SdfNet:
         K('nero_wgrad_finish', self.tmp_row, 1, 1, 256, self.tmp_b, 256, 0, 1, None, 1.0, l8.weight_v.detach(), l8.weight_g.detach(),
           l8.weight_v.grad, l8.weight_g.grad, l8.bias.grad, None, 0.0)
 
-    def value_backward(self, ws, w, Hs, X0, dsdf, m_ptr, m_cap, AB):
-        """Backward of a value-only pass (sdf output only; used for the step<1000 sdf regulariser)."""
-        raise NotImplementedError
+    def value_forward(self, X0, H, out, m_ptr, m_cap):
+        """SDF value with saved activations H[1..8] (step<1000 regulariser points, renderer.py:591-594)."""
+        Hs = [H[1], H[2], H[3], H[4], H[5], H[6], H[7], H[8]]
+        if USE_CHAIN:
+            self.hidden_forward(X0, Hs, H[4], m_ptr, m_cap, heads=[CL(self.L8s, EK_BIAS_GENERIC, 1, save=Mat(out), write_a=False)])
+        else:
+            self.hidden_forward(X0, Hs, H[4], m_ptr, m_cap)
+            linear(Mat(H[8]), self.L8s, Mat(out), 1, m_ptr=m_ptr, m_cap=m_cap)
+
+    def value_backward(self, ws, X0, H, dsdf, AB, scratch, m_ptr, m_cap):
+        """Backward of value_forward: dsdf [.,1] -> parameter grads.  abar_7 = dsdf * sigma_7 * W8[0,:], then the
+        plain reverse chain abar_{k-1} = sigma_{k-1} * (W_k^T abar_k), then dW_k = abar_k^T h_k."""
+        kw = dict(m_ptr=m_ptr, m_cap=m_cap)
+        K('nero_dact_times_row', H[8], 256, self.L8s.w_eff, scratch, 256, 256, m_ptr, m_cap)
+        AB[7].zero_()
+        K('nero_row_axpy', dsdf, dsdf.stride(0), scratch, 256, AB[7], 256, 256, m_ptr, m_cap)
+        ls = []
+        for k in range(7, 0, -1):
+            if k == 4:
+                ls.append(CL(self.L[4], EK_DACT_SOFTPLUS, 217, transposed=True, oscale=INV_SQRT2, H=Mat(H[4]), hscale=SQRT2, save=Mat(AB[3])))
+            else:
+                ls.append(CL(self.L[k], EK_DACT_SOFTPLUS, 256, transposed=True, H=Mat(H[k]), save=Mat(AB[k - 1])))
+        if USE_CHAIN:
+            chain(Mat(AB[7]), 256, ls, m_ptr, m_cap)
+        else:
+            for k in range(7, 0, -1):
+                if k == 4:
+                    linear(Mat(AB[4]), self.L[4], Mat(AB[3]), 217, transposed=True, mode=EPI_MUL_DACT, oscale=INV_SQRT2, H=Mat(H[4]),
+                           hscale=SQRT2, dact=ACT_SOFTPLUS100, **kw)
+                else:
+                    linear(Mat(AB[k]), self.L[k], Mat(AB[k - 1]), 256, transposed=True, mode=EPI_MUL_DACT, H=Mat(H[k]),
+                           dact=ACT_SOFTPLUS100, **kw)
+        ls_ = self.sp.layers()
+        for k in range(8):
+            Hin = Mat(X0) if k == 0 else Mat(H[k])
+            wgrad(ws, Mat(AB[k]), self.nout[k], Hin, self.L[k].k_valid, self.L[k], ls_[k].weight_v.grad, ls_[k].weight_g.grad,
+                  ls_[k].bias.grad, **kw)
+        l8 = ls_[8]
+        self.tmp_row.zero_()
+        self.tmp_b.zero_()
+        ops.colsum(Mat(H[8]), 256, self.tmp_row, w=Mat(dsdf), m_ptr=m_ptr, m_cap=m_cap)
+        ops.colsum(Mat(dsdf), 1, self.tmp_b, m_ptr=m_ptr, m_cap=m_cap)
+        K('nero_wgrad_finish', self.tmp_row, 1, 1, 256, self.tmp_b, 256, 0, 1, None, 1.0, l8.weight_v.detach(), l8.weight_g.detach(),
+          l8.weight_v.grad, l8.weight_g.grad, l8.bias.grad, None, 0.0)
 
 
 class NerfNet:
@@ -466,6 +507,35 @@ class ShapeEngine:
         self.cap = (R, S)
         self.bw_ready = False
 
+    def _alloc_reg(self):
+        if 'REG_H' in self.w:
+            return
+        R, S = self.cap
+        cap = R * S
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=self.dev)
+        self.w.update(REG_CNT=z(R, dt=torch.int32), REG_OFF=z(R, dt=torch.int32), REG_N=z(1, dt=torch.int32), REG_DUMMY=z(R, dt=torch.int32),
+                      REG_DUMMY1=z(1, dt=torch.int32), REG_PTS=z(cap, 4), REG_X0=z(cap, 64), REG_SDF=z(cap, 1), REG_DSDF=z(cap, 1))
+        self.w['REG_H'] = [None] + [z(cap, 256) for _ in range(8)]
+
+    def reg_forward(self, rays_o, rays_d, z_vals):
+        """sdf_pts / sdf_vals of renderer.py:591-594 (value-only SDF pass on every mid-point with |p| < 1.2)."""
+        R, S = z_vals.shape
+        self._alloc_reg()
+        w = self.w
+        K('nero_reg_prepare', rays_o, rays_d, z_vals, R, S, 1.2, w['REG_CNT'], w['REG_DUMMY'], w['REG_OFF'], w['REG_DUMMY'], w['REG_N'],
+          w['REG_DUMMY1'])
+        K('nero_reg_fill', rays_o, rays_d, z_vals, R, S, 1.2, w['REG_OFF'], w['REG_PTS'], w['REG_X0'], 64, w['REG_H'][4], 256)
+        self.sdf.value_forward(w['REG_X0'], w['REG_H'], w['REG_SDF'], w['REG_N'], R * S)
+
+    def reg_backward(self, d_sdf_vals):
+        self._alloc_backward()
+        self.grads.ensure()
+        w = self.w
+        k = d_sdf_vals.shape[0]
+        w['REG_DSDF'][:k, 0].copy_(d_sdf_vals)
+        cap = self.cap[0] * self.cap[1]
+        self.sdf.value_backward(self.ws, w['REG_X0'], w['REG_H'], w['REG_DSDF'], w['ABAR'], w['dHa'], w['REG_N'], cap)
+
     def _alloc_backward(self):
         if self.bw_ready:
             return
@@ -564,8 +634,15 @@ class ShapeEngine:
         if ops.DRY_RUN:
             w['n_in'].fill_(100)
             w['OCC_COUNT'].fill_(min(3000, cap))
-        counts = torch.cat([w['n_in'], w['OCC_COUNT']]).tolist()    # the one host sync of the forward pass
+        with_reg = step < 1000
+        if with_reg:
+            self.reg_forward(rays_o, rays_d, z_vals)
+            w = self.w
+            if ops.DRY_RUN:
+                w['REG_N'].fill_(50)
+        counts = torch.cat([w['n_in'], w['OCC_COUNT'], w['REG_N'] if with_reg else w['n_out']]).tolist()   # the one host sync
         N_in = counts[0]
+        self.n_reg = counts[2] if with_reg else 0
         if occ_on:
             P = self._occ_forward(counts[1], perm)
         self.state = dict(R=R, S=S, N_in=N_in, P=P, rays_d=rays_d, hp=hp, car=float(cos_anneal_ratio), step=step)

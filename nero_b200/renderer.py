@@ -26,12 +26,16 @@ class _RenderCoreFn(torch.autograd.Function):
         w = engine.w
         gerr = w['GERR'][:n_in].clone() if n_in > 0 else torch.zeros(1, device=rgb.device)
         loss_occ = (w['OCC_LOSS'][0] / P).clone() if P > 0 else torch.zeros(1, device=rgb.device)
-        ctx.engine, ctx.P, ctx.n_in, ctx.nparams = engine, P, n_in, len(params)
-        return rgb, gerr, loss_occ
+        n_reg = engine.n_reg
+        sdf_vals = w['REG_SDF'][:n_reg, 0].clone() if n_reg > 0 else torch.zeros(0, device=rgb.device)
+        ctx.engine, ctx.P, ctx.n_in, ctx.nparams, ctx.n_reg = engine, P, n_in, len(params), n_reg
+        return rgb, gerr, loss_occ, sdf_vals
 
     @staticmethod
-    def backward(ctx, d_rgb, d_gerr, d_occ):
+    def backward(ctx, d_rgb, d_gerr, d_occ, d_sdf_vals):
         e = ctx.engine
+        if ctx.n_reg > 0:
+            e.reg_backward(d_sdf_vals.contiguous())      # uses ABAR/dHa as scratch: must run before the main backward
         dscale = (d_occ.reshape(()) / ctx.P) if ctx.P > 0 else None
         e.render_core_backward(d_rgb, d_gerr if ctx.n_in > 0 else None, dscale)
         return (None,) * (8 + ctx.nparams)
@@ -145,19 +149,20 @@ class NeROShapeRenderer(nn.Module):
         if not is_train:
             raise NotImplementedError('validation render (compute_validation_info) is not part of the B200 hot path yet')
         e = self.engine
-        if step < 1000:
-            raise NotImplementedError('init_sdf_reg outputs (step < 1000) are not implemented in the B200 path yet')
         if not getattr(self, '_weights_fresh', False):
             e.prepare_weights()          # render_core called on its own: fold weight-norm / rebuild operand images
         self._weights_fresh = False
         params = [p for p in self.parameters()]
-        rgb, gerr, loss_occ = _RenderCoreFn.apply(e, rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(),
+        rgb, gerr, loss_occ, sdf_vals = _RenderCoreFn.apply(e, rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(),
                                                   human_poses.contiguous(), float(cos_anneal_ratio), int(step), perm, *params)
         outputs = {'ray_rgb': rgb, 'gradient_error': gerr}
         inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)
         if self.cfg['freeze_inv_s_step'] is not None and step < self.cfg['freeze_inv_s_step']:
             inv_s = inv_s.detach()
         outputs['std'] = torch.mean(1 / inv_s) if e.state['N_in'] > 0 else torch.zeros(1, device=rgb.device)
+        if step < 1000:       # network/renderer.py:591-594 (consumed by InitSDFRegLoss, network/loss.py:98-120)
+            outputs['sdf_pts'] = e.w['REG_PTS'][:e.n_reg, :3].clone()
+            outputs['sdf_vals'] = sdf_vals
         if self.cfg['apply_occ_loss']:
             outputs['loss_occ'] = loss_occ
         return outputs

@@ -93,7 +93,7 @@ rep('loss_occ', out['loss_occ'].reshape(-1), out_o['loss_occ'].reshape(-1))
 if 'sh_human_light' in it and torch.is_tensor(it['sh_human_light']):
     rep('human hl', w['OUTS'][:N, 28:31] * w['GEO'][:N, 7:8], it['sh_human_light'])
 
-loss = torch.mean(net.compute_rgb_loss(out['ray_rgb'], cu['rgb'])) + torch.mean(out['gradient_error'] * 0.1) + torch.mean(out['loss_occ'])
+loss = O.training_loss(out, cu['rgb'], c, step)
 print('loss', float(loss), 'oracle', float(loss_o), 'golden', float(g[f's{step}_loss']))
 loss.backward()
 (None if os.environ.get('NERO_DRY_RUN') else torch.cuda.synchronize())

@@ -64,8 +64,6 @@ def test_render_core_matches_reference(name):
     z = t(g['z_vals']).to(DEV)
     names = [str(n) for n in g['param_names']]
     for step in FIXTURE_STEPS[name]:
-        if step < 1000:
-            continue   # init_sdf_reg outputs: see test_sdf_reg_path
         net.zero_grad()
         out = net.render_core(r['rays_o'], r['rays_d'], z, r['human_poses'], O.get_anneal_val(c, step), step)
         pre = f's{step}_'
@@ -73,7 +71,10 @@ def test_render_core_matches_reference(name):
         allclose(out['gradient_error'], g[pre + 'gradient_error'], 2e-3, 2e-5, 'gradient_error')
         allclose(out['std'], g[pre + 'std'], 1e-6, 0, 'std')
         allclose(out['loss_occ'], g[pre + 'loss_occ'], 1e-3, 1e-6, 'loss_occ')
-        loss = torch.mean(net.compute_rgb_loss(out['ray_rgb'], r['rgb'])) + torch.mean(out['gradient_error'] * 0.1) + torch.mean(out['loss_occ'])
+        if step < 1000:
+            allclose(out['sdf_pts'], g[pre + 'sdf_pts'], 1e-5, 1e-6, 'sdf_pts')
+            allclose(out['sdf_vals'], g[pre + 'sdf_vals'], 1e-4, 2e-5, 'sdf_vals')
+        loss = O.training_loss(out, r['rgb'], c, step)      # the YAML loss set incl. init_sdf_reg for step < 1000
         assert abs(float(loss) - float(g[pre + 'loss'])) <= 1e-4 * abs(float(g[pre + 'loss']))
         loss.backward()
         torch.cuda.synchronize()
