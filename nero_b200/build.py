@@ -24,17 +24,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), lib_out=None):
+    if lib_out is None and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build' if lib_out is None else 'build_' + os.path.basename(lib_out))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + ['-c', src, '-o', obj]
+        cmd = [NVCC] + FLAGS + list(extra_flags) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True
     for src, pr in procs:
@@ -44,9 +44,9 @@ def build(force=False, verbose=False):
         ok = ok and pr.returncode == 0
     if not ok:
         raise RuntimeError('nvcc failed')
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [NVCC, '-shared', '-o', lib_out or LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
-    return LIB
+    return lib_out or LIB
 
 
 if __name__ == '__main__':

@@ -3,6 +3,10 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#ifndef NERO_PF_MODE
+#define NERO_PF_MODE 2   // aux-operand L2 prefetch: 0 off, 1 per-sector prefetch.global.L2, 2 bulk prefetch per row
+#endif
+
 namespace nero {
 
 // compile-time epilogue kinds
@@ -87,6 +91,45 @@ __device__ __forceinline__ void load_block16(const float* __restrict__ g, int ld
   }
   __syncwarp();
 }
+// split version of load_block16 for software pipelining: issue the coalesced global loads now ...
+__device__ __forceinline__ void issue_block16(const float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec, int lane,
+                                              float4 (&x)[4]) {
+  if (vec && rows_valid >= 32 && cols_valid >= 16) {
+    const float* src = g + size_t(lane >> 2) * ld + (lane & 3) * 4;
+    const size_t ld8 = size_t(ld) * 8;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) x[it] = __ldg(reinterpret_cast<const float4*>(src + it * ld8));
+  } else {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2), q = (lane & 3) * 4;
+      x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows_valid) {
+        const float* p = g + size_t(row) * ld + q;
+        if (vec && q + 3 < cols_valid) x[it] = *reinterpret_cast<const float4*>(p);
+        else {
+          if (q < cols_valid) x[it].x = p[0];
+          if (q + 1 < cols_valid) x[it].y = p[1];
+          if (q + 2 < cols_valid) x[it].z = p[2];
+          if (q + 3 < cols_valid) x[it].w = p[3];
+        }
+      }
+    }
+  }
+}
+// ... and transpose them into the "lane = row" register layout later
+__device__ __forceinline__ void finish_block16(const float4 (&x)[4], float* stage, int lane, float* r) {
+  float* sdst = stage + (lane >> 2) * kStagePitch + (lane & 3) * 4;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) *reinterpret_cast<float4*>(sdst + it * 8 * kStagePitch) = x[it];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 y = *reinterpret_cast<const float4*>(stage + lane * kStagePitch + j * 4);
+    r[4 * j] = y.x; r[4 * j + 1] = y.y; r[4 * j + 2] = y.z; r[4 * j + 3] = y.w;
+  }
+  __syncwarp();
+}
 // the reverse: registers ("lane = row") -> coalesced global store of columns [0, cols_valid)
 __device__ __forceinline__ void store_block16(float* __restrict__ g, int ld, int rows_valid, int cols_valid, bool vec,
                                               float* stage, int lane, const float* r) {
@@ -125,14 +168,23 @@ __device__ __forceinline__ void store_block16(float* __restrict__ g, int ld, int
   }
   __syncwarp();
 }
-// prefetch the [32 rows x ncols] window of an aux matrix into L2 (one 128-byte line per lane per step)
+// prefetch the [32 rows x ncols] window of an aux matrix into L2: one bulk prefetch (UBLKPF) per row segment
 __device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ g, int ld, int rows_valid, int ncols, int lane) {
-  if (!g || rows_valid <= 0) return;
-  const int lines = (ncols * 4 + 127) / 128;
-  for (int i = lane; i < rows_valid * lines; i += 32) {
-    const int r = i / lines, l = i % lines;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + size_t(r) * ld + l * 32));
+  if (!g || rows_valid <= 0 || ncols <= 0) return;
+#if NERO_PF_MODE == 2
+  const uint32_t bytes = uint32_t(((ncols * 4) + 15) & ~15);
+  if (lane < rows_valid) {
+    const float* p = g + size_t(lane) * ld;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
   }
+#elif NERO_PF_MODE == 1
+  const int sectors = (ncols * 4 + 31) / 32;            // one prefetch per 32-byte sector
+  for (int i = lane; i < rows_valid * sectors; i += 32) {
+    const int r = i / sectors, l = i % sectors;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + size_t(r) * ld + l * 8));
+  }
+#endif
 }
 __device__ __forceinline__ bool vec_ok(const float* p, int ld) {
   return ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
