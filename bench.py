@@ -226,18 +226,21 @@ def run_ours(args):
             'step_tensor_frac_of_bf16_peak': F / (ms * 1e-3) / 1e12 / peak_tf,
             'roofline': None, 'cpu_baseline': None,
         }
-        if prof is not None:
-            ach = prof['flops'] / prof['seconds'] / 1e12
+        if prof is not None and prof['reverse_sweep'] is not None:
+            one = prof['reverse_sweep']
+            ach = one['flops'] / one['seconds'] / 1e12
             traffic = None
-            tp = os.path.join(ROOT, 'profiles', 'r01_linear256_traffic.json')
+            tp = os.path.join(ROOT, 'profiles', 'r01_chain_traffic.json')
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get('dram_bytes_per_launch')
-            line['roofline'] = {'bound': 'tensor', 'kernel': 'umma_linear_kernel<256> (all launches of one training step)',
+            line['roofline'] = {'bound': 'tensor', 'kernel': 'umma_chain_kernel: SDF reverse-sweep chain (8 fused 256-wide layers, one launch)',
                                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                                 'frac_of_split3_ceiling': ach / (peak_tf / 3.0), 'peak_source': which + ' bf16 sustained',
-                                'launches': prof['launches'], 'avg_launch_us': prof['seconds'] / prof['launches'] * 1e6,
-                                'traffic': traffic,
-                                'note': 'achieved counts ALGORITHMIC fp32 GEMM flops (2*M*K*N of the un-padded layer); the '
+                                'launch_us': one['seconds'] * 1e6, 'rows': one['rows'], 'traffic': traffic,
+                                'all_chain_launches': {'launches': prof['launches'], 'total_ms': prof['seconds'] * 1e3,
+                                                       'achieved': prof['flops'] / prof['seconds'] / 1e12,
+                                                       'frac': prof['flops'] / prof['seconds'] / 1e12 / peak_tf},
+                                'note': 'achieved counts ALGORITHMIC fp32 GEMM flops (2*M*K*N of the un-padded layers); the '
                                         'split-bf16 scheme issues 3 bf16 MMAs per product, so 1/3 of peak is its ceiling'}
         if not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline(rays_n=128, steps=1)
@@ -247,48 +250,32 @@ def run_ours(args):
 
 
 def profile_linear(net, r, car):
-    """One extra (untimed-for-the-headline) training step with a CUDA-event pair around every tcgen05 linear launch
-    with a 256-wide tile, recorded on the launch stream."""
+    """One extra training step with a CUDA-event pair (on the launch stream) around every fused MLP-chain launch
+    (ops.PROFILE hook).  Returns the aggregate over all chain launches and the SDF reverse-sweep chain alone (the
+    launch whose ncu capture is committed under profiles/)."""
     from nero_b200 import ops
-    R = r['rays_o'].shape[0]
-    recs = []
-    orig = ops.lib.nero_linear
-    state = net.engine.state
-
-    class Wrapped:
-        def __call__(self, *a):
-            n_pad = a[4]
-            if n_pad != 256:
-                return orig(*a)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            rc = orig(*a)
-            e1.record()
-            recs.append((e0, e1, a))
-            return rc
-    ops.lib.nero_linear = Wrapped()
+    ops.PROFILE = []
     try:
         net.zero_grad()
         z = net.sample_ray(r['rays_o'], r['rays_d'], r['near'], r['far'], 0)
         out = net.render_core(r['rays_o'], r['rays_d'], z, r['human_poses'], car, STEP)
         training_loss(net, out, r['rgb']).backward()
         torch.cuda.synchronize()
+        recs = ops.PROFILE
     finally:
-        ops.lib.nero_linear = orig
-    n_in, n_out = state['N_in'], int(net.engine.w['n_out'].item())
-    flops, secs = 0.0, 0.0
-    for e0, e1, a in recs:
-        m_ptr, m_cap, k_valid, ncol = a[-3], a[-2], a[2], a[10]
-        mp = m_ptr.value if hasattr(m_ptr, 'value') else None
-        if mp is None or mp == 0:
-            M = m_cap
-        elif mp == net.engine.w['n_in'].data_ptr():
-            M = n_in
-        else:
-            M = n_out
-        flops += 2.0 * M * k_valid * ncol
-        secs += e0.elapsed_time(e1) * 1e-3
-    return {'flops': flops, 'seconds': secs, 'launches': len(recs)}
+        ops.PROFILE = None
+    w = net.engine.w
+    counts = {w['n_in'].data_ptr(): net.engine.state['N_in'], w['n_out'].data_ptr(): int(w['n_out'].item())}
+    tot_f = tot_s = 0.0
+    one = None
+    for tag, e0, e1, fl_row, mp, m_cap in recs:
+        M = m_cap if mp is None else counts.get(mp, m_cap)
+        sec = e0.elapsed_time(e1) * 1e-3
+        tot_f += fl_row * M
+        tot_s += sec
+        if tag == 'sdf_reverse_sweep':
+            one = {'flops': fl_row * M, 'seconds': sec, 'rows': M}
+    return {'flops': tot_f, 'seconds': tot_s, 'launches': len(recs), 'reverse_sweep': one}
 
 
 def cpu_baseline(rays_n=128, steps=1, threads=None):

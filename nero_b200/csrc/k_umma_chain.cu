@@ -68,58 +68,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// FULL 32x16 blocks (all rows / columns valid, 16-byte aligned): branch-free staged transposes on 32-bit smem addresses.
-// lane = row layout r[16]  <->  coalesced global (8 rows x 64 B per instruction)
-__device__ __forceinline__ void fast_store16(float* __restrict__ g, size_t ld8, uint32_t st_row, uint32_t st_co, const float* r) {
-  sts128(st_row, r[0], r[1], r[2], r[3]); sts128(st_row + 16, r[4], r[5], r[6], r[7]);
-  sts128(st_row + 32, r[8], r[9], r[10], r[11]); sts128(st_row + 48, r[12], r[13], r[14], r[15]);
-  __syncwarp();
-  const float4 x0 = lds128(st_co), x1 = lds128(st_co + 8 * kStagePitch * 4), x2 = lds128(st_co + 16 * kStagePitch * 4),
-               x3 = lds128(st_co + 24 * kStagePitch * 4);
-  *reinterpret_cast<float4*>(g) = x0;
-  *reinterpret_cast<float4*>(g + ld8) = x1;
-  *reinterpret_cast<float4*>(g + 2 * ld8) = x2;
-  *reinterpret_cast<float4*>(g + 3 * ld8) = x3;
-  __syncwarp();
-}
-__device__ __forceinline__ void fast_issue16(const float* __restrict__ g, size_t ld8, float4 (&x)[4]) {
-  x[0] = __ldg(reinterpret_cast<const float4*>(g));
-  x[1] = __ldg(reinterpret_cast<const float4*>(g + ld8));
-  x[2] = __ldg(reinterpret_cast<const float4*>(g + 2 * ld8));
-  x[3] = __ldg(reinterpret_cast<const float4*>(g + 3 * ld8));
-}
-__device__ __forceinline__ void fast_finish16(const float4 (&x)[4], uint32_t st_row, uint32_t st_co, float* r) {
-  sts128(st_co, x[0].x, x[0].y, x[0].z, x[0].w);
-  sts128(st_co + 8 * kStagePitch * 4, x[1].x, x[1].y, x[1].z, x[1].w);
-  sts128(st_co + 16 * kStagePitch * 4, x[2].x, x[2].y, x[2].z, x[2].w);
-  sts128(st_co + 24 * kStagePitch * 4, x[3].x, x[3].y, x[3].z, x[3].w);
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 y = lds128(st_row + 16 * j);
-    r[4 * j] = y.x; r[4 * j + 1] = y.y; r[4 * j + 2] = y.z; r[4 * j + 3] = y.w;
-  }
-  __syncwarp();
-}
-
 // write 16 fp32 values of this lane's row (columns c0..c0+15 of the next A operand) as packed split-bf16 into TMEM
 __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const float* y) {
   uint32_t hi[8], lo[8];
@@ -139,86 +87,11 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
   // when this layer feeds the next one, every 16-column block the next layer's MMAs read must be defined
   const int nblk_a = L.write_a ? max(L.a_blocks, nblk) : 0;
   const int nb_loop = max(nblk, nblk_a);
-  // ---- hoisted, register-resident copies of the layer descriptor (the asm memory clobbers would otherwise force
-  //      a constant-bank reload of every field at every use)
-  const float oscale = L.oscale, hscale = L.hscale;
-  float* const g_save = L.save; const float* const g_H = L.H; const float* const g_add = L.addend; const float* const g_V = L.V;
-  float* const g_out2 = L.out2;
-  const int ld_save = L.ld_save, ldh = L.ldh, ldadd = L.ldadd, ldv = L.ldv, ldo2 = L.ldo2;
-  const bool fast_rows = rows_valid >= 32 && (!g_save || v_save) && (!g_H || vec_ok(g_H, ldh)) && (!g_add || vec_ok(g_add, ldadd)) &&
-                         (!g_V || vec_ok(g_V, ldv)) && (!g_out2 || vec_ok(g_out2, ldo2)) && !L.tail;
-  const uint32_t st_base = smem_u32(stg);
-  const uint32_t st_row = st_base + uint32_t(lane) * (kStagePitch * 4);                                    // own row
-  const uint32_t st_co = st_base + uint32_t(lane >> 2) * (kStagePitch * 4) + uint32_t(lane & 3) * 16;     // coalesced view
-  const size_t co_off = size_t(lane >> 2);
-  const int co_col = (lane & 3) * 4;
-  const uint32_t sb_u32 = smem_u32(s_bias);
 #pragma unroll 1
   for (int b = third; b < nb_loop; b += 3) {
     const int c0 = b * 16;
     float r[16];
-    if (fast_rows && b < nblk && c0 + 16 <= nmain) {
-      // ======================= fast path: full block =======================
-      float v[16];
-      float4 hraw[4], araw[4], vraw[4];
-      if constexpr (!kBias) {
-        if constexpr (KIND != EK_DACT_NONE) fast_issue16(g_H + (size_t(row0) + co_off) * ldh + c0 + co_col, size_t(ldh) * 8, hraw);
-        if (g_add) fast_issue16(g_add + (size_t(row0) + co_off) * ldadd + c0 + co_col, size_t(ldadd) * 8, araw);
-        if constexpr (KIND == EK_TANGENT) fast_issue16(g_V + (size_t(row0) + co_off) * ldv + c0 + co_col, size_t(ldv) * 8, vraw);
-      }
-      tmem_ld16(tmem_lane_base + kAccCol + c0, v);
-      tmem_ld_wait();
-      if constexpr (kBias) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 bq = lds128(sb_u32 + uint32_t(c0 + 4 * q) * 4);
-          v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float y;
-          if constexpr (KIND == EK_BIAS_SOFTPLUS) {
-            const float z = 100.0f * v[j];
-            const float t = ex2_approx(fminf(z, 20.0f) * 1.4426950408889634f);
-            const float h = lg2_approx(1.0f + t) * (0.6931471805599453f * 0.01f);
-            y = z > 20.0f ? v[j] : h;
-          } else if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(v[j], 0.0f);
-          else y = apply_act(v[j], L.act, L.act_param);
-          r[j] = oscale * y;
-        }
-      } else {
-        float s[16];
-        if constexpr (KIND == EK_DACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = oscale * v[j];
-        } else {
-          fast_finish16(hraw, st_row, st_co, s);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if constexpr (KIND == EK_DACT_RELU) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
-            else {
-              const float z = 100.0f * hscale * s[j];
-              s[j] = z > 20.0f ? 1.0f : 1.0f - ex2_approx(-z * 1.4426950408889634f);
-            }
-            r[j] = oscale * s[j] * v[j];
-          }
-        }
-        if (g_add) {
-          float a[16];
-          fast_finish16(araw, st_row, st_co, a);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] += a[j];
-        }
-        if constexpr (KIND == EK_TANGENT) {
-          float vv[16];
-          fast_finish16(vraw, st_row, st_co, vv);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vv[j] = 100.0f * (1.0f - s[j]) * vv[j] * v[j];
-          fast_store16(g_out2 + (size_t(row0) + co_off) * ldo2 + c0 + co_col, size_t(ldo2) * 8, st_row, st_co, vv);
-        }
-      }
-      if (g_save) fast_store16(g_save + (size_t(row0) + co_off) * ld_save + c0 + co_col, size_t(ld_save) * 8, st_row, st_co, r);
-    } else if (b < nblk && c0 < L.ncol_out) {
+    if (b < nblk && c0 < L.ncol_out) {
       float v[16];
       tmem_ld16(tmem_lane_base + kAccCol + c0, v);
       tmem_ld_wait();

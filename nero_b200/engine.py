@@ -180,7 +180,7 @@ class SdfNet:
                   CL(self.L[3], EK_BIAS_SOFTPLUS, 217, oscale=INV_SQRT2, save=sv(H4buf), csrc=Mat(H4buf)),
                   CL(self.L[4], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[4])), CL(self.L[5], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[5])),
                   CL(self.L[6], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[6])), CL(self.L[7], EK_BIAS_SOFTPLUS, 256, save=sv(Hs[7]))]
-            chain(Mat(X0), self.L[0].k_valid, ls + (heads or []), m_ptr, m_cap)
+            chain(Mat(X0), self.L[0].k_valid, ls + (heads or []), m_ptr, m_cap, tag='sdf_forward' if save else 'sdf_forward_nosave')
             return
         linear(Mat(X0), self.L[0], Mat(Hs[0]), 256, **kw)
         linear(Mat(Hs[0]), self.L[1], Mat(Hs[1]), 256, **kw)
@@ -220,7 +220,7 @@ class SdfNet:
                 else:
                     ls.append(CL(self.L[k], EK_DACT_SOFTPLUS, 256, transposed=True, H=Mat(H[k]), save=Mat(V[k - 1])))
             ls.append(CL(self.L[0], EK_DACT_NONE, 39, transposed=True, save=Mat(w['U0'])))
-            chain(Mat(V[7]), 256, ls, m_ptr, m_cap)
+            chain(Mat(V[7]), 256, ls, m_ptr, m_cap, tag='sdf_reverse_sweep')
             K('nero_pe_grad', w['X0'], 64, w['U0'], 64, w['USKIP'], 64, w['G'], m_ptr, m_cap)
             return
         self.hidden_forward(w['X0'], Hs, H[4], m_ptr, m_cap)
@@ -254,7 +254,7 @@ class SdfNet:
                                  out2=Mat(AB[3]), save=Mat(UB[4]), csrc=Mat(UB[4])))
                 else:
                     ls.append(CL(self.L[k], EK_TANGENT, 256, use_bias=False, H=Mat(H[k + 1]), V=Mat(V[k]), out2=Mat(AB[k]), save=Mat(UB[k + 1])))
-            chain(Mat(UB[0]), self.L[0].k_valid, ls, m_ptr, m_cap)
+            chain(Mat(UB[0]), self.L[0].k_valid, ls, m_ptr, m_cap, tag='sdf_tangent_sweep')
             # value backward: abar_7 = sigma_7*(W8f^T dfeat) + q_7 + dsdf*v_7 (v_7 = sigma_7*W8[0,:] from the reverse sweep);
             # abar_{k-1} = sigma_{k-1} * (W_k^T abar_k) + q_{k-1}
             K('nero_row_axpy', Mat(dY8, Y8_SDF), Y8_LD, V[7], 256, AB[7], 256, 256, m_ptr, m_cap)
@@ -265,7 +265,7 @@ class SdfNet:
                                  addend=Mat(AB[3]), save=Mat(AB[3])))
                 else:
                     ls.append(CL(self.L[k], EK_DACT_SOFTPLUS, 256, transposed=True, H=Mat(H[k]), addend=Mat(AB[k - 1]), save=Mat(AB[k - 1])))
-            chain(Mat(dY8), 256, ls, m_ptr, m_cap)
+            chain(Mat(dY8), 256, ls, m_ptr, m_cap, tag='sdf_value_backward')
         else:
             for k in range(8):
                 A = Mat(UB[k])

@@ -351,7 +351,10 @@ def chain_layer(layer: PreparedLayer, kind, ncol_out, *, transposed=False, save:
                 write_a=write_a, csrc=csrc, use_bias=use_bias)
 
 
-def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None):
+PROFILE = None   # bench.py: list collecting (tag, event0, event1, flops_per_row, m_ptr_addr, m_cap) per chain launch
+
+
+def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None, tag=''):
     """Run consecutive layers on each 128-row tile with the A operand kept in TMEM (k_umma_chain.cu)."""
     global launch_count
     assert 1 <= len(layers) <= 10
@@ -394,9 +397,20 @@ def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None):
     if DRY_RUN:
         assert A0.c0 % 4 == 0 and A0.ld % 4 == 0 and A0.c0 + P.k_valid0 <= A0.t.shape[1]
         return
+    if PROFILE is not None:
+        fl = 0.0
+        for d in layers:
+            lay = d['layer']
+            kdim = lay.nrows if d['transposed'] else lay.K
+            fl += 2.0 * kdim * d['ncol_out']
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = lib.nero_chain(ctypes.byref(P), _stream())
     _check(rc, 'nero_chain')
     launch_count += 1
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((tag, e0, e1, fl, None if m_ptr is None else m_ptr.data_ptr(), m_cap))
 
 
 def _chain_unfused(A0, k_valid0, layers, m_ptr, m_cap):
