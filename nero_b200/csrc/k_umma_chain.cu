@@ -97,12 +97,13 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
       tmem_ld_wait();
       if constexpr (kBias) {
 #pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
+        if constexpr (KIND == EK_BIAS_SOFTPLUS) softplus100_fast16(v);
+#pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float x = v[j] + s_bias[c0 + j];
-          float y;
-          if constexpr (KIND == EK_BIAS_SOFTPLUS) y = softplus100_fast(x);
-          else if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(x, 0.0f);
-          else y = apply_act(x, L.act, L.act_param);
+          float y = v[j];
+          if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
+          else if constexpr (KIND == EK_BIAS_GENERIC) y = apply_act(y, L.act, L.act_param);
           r[j] = L.oscale * y;
         }
       } else {
@@ -113,10 +114,11 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
           for (int j = 0; j < 16; ++j) s[j] = 1.0f;
         } else {
           load_block16(L.H + size_t(row0) * L.ldh + c0, L.ldh, rows_valid, cm, vec_ok(L.H, L.ldh), stg, lane, s);
+          if constexpr (KIND == EK_DACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if constexpr (KIND == EK_DACT_RELU) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
-            else s[j] = dsoftplus100_from_h_fast(s[j] * L.hscale);
+            for (int j = 0; j < 16; ++j) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
+          } else {
+            dsoftplus100_from_h_fast16(s, L.hscale);
           }
         }
 #pragma unroll
@@ -164,6 +166,10 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
   }
 }
 
+// FAM: 0 = bias/activation epilogues (forward chains), 1 = derivative-product epilogues (gradient sweeps), 2 = tangent
+// sweep.  One instantiation per family keeps the register pressure of each kernel low enough for ptxas to overlap
+// the sixteen independent MUFU chains of a block instead of serialising them through one register.
+template <int FAM>
 __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -236,14 +242,16 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         acc_phase ^= 1;
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
-        switch (L.kind) {
-          case EK_BIAS_SOFTPLUS: chain_epilogue_layer<EK_BIAS_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
-          case EK_BIAS_RELU: chain_epilogue_layer<EK_BIAS_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
-          case EK_BIAS_GENERIC: chain_epilogue_layer<EK_BIAS_GENERIC>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
-          case EK_DACT_SOFTPLUS: chain_epilogue_layer<EK_DACT_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
-          case EK_DACT_RELU: chain_epilogue_layer<EK_DACT_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
-          case EK_DACT_NONE: chain_epilogue_layer<EK_DACT_NONE>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
-          default: chain_epilogue_layer<EK_TANGENT>(L, tl, row0, rows_valid, third, lane, stg, sb); break;
+        if constexpr (FAM == 0) {
+          if (L.kind == EK_BIAS_SOFTPLUS) chain_epilogue_layer<EK_BIAS_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          else if (L.kind == EK_BIAS_RELU) chain_epilogue_layer<EK_BIAS_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          else chain_epilogue_layer<EK_BIAS_GENERIC>(L, tl, row0, rows_valid, third, lane, stg, sb);
+        } else if constexpr (FAM == 1) {
+          if (L.kind == EK_DACT_SOFTPLUS) chain_epilogue_layer<EK_DACT_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          else if (L.kind == EK_DACT_RELU) chain_epilogue_layer<EK_DACT_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          else chain_epilogue_layer<EK_DACT_NONE>(L, tl, row0, rows_valid, third, lane, stg, sb);
+        } else {
+          chain_epilogue_layer<EK_TANGENT>(L, tl, row0, rows_valid, third, lane, stg, sb);
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -318,15 +326,27 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
     if (L.kind == EK_TANGENT && (!L.H || !L.V || !L.out2)) return NERO_ERR_ARG;
     if ((L.kind == EK_DACT_SOFTPLUS || L.kind == EK_DACT_RELU) && !L.H) return NERO_ERR_ARG;
   }
+  int fam = -1;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int k = p.L[l].kind;
+    const int f = k <= EK_BIAS_GENERIC ? 0 : (k == EK_TANGENT ? 2 : 1);
+    if (fam >= 0 && f != fam) return NERO_ERR_ARG;   // a chain is homogeneous: forward, gradient sweep or tangent sweep
+    fam = f;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes) != cudaSuccess) return NERO_ERR_CUDA;
+    if (cudaFuncSetAttribute(umma_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(umma_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(umma_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes) != cudaSuccess)
+      return NERO_ERR_CUDA;
     attr_set = true;
   }
   const int tiles_cap = (p.m_cap + CH_BM - 1) / CH_BM;
   if (tiles_cap <= 0) return NERO_OK;
   const int grid = tiles_cap < kNumSMs ? tiles_cap : kNumSMs;
-  umma_chain_kernel<<<grid, kChThreads, kChSmemBytes, stream>>>(p);
+  if (fam == 0) umma_chain_kernel<0><<<grid, kChThreads, kChSmemBytes, stream>>>(p);
+  else if (fam == 1) umma_chain_kernel<1><<<grid, kChThreads, kChSmemBytes, stream>>>(p);
+  else umma_chain_kernel<2><<<grid, kChThreads, kChSmemBytes, stream>>>(p);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

@@ -130,12 +130,13 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
         float r[16];
         if constexpr (kBias) {
 #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
+          if constexpr (EPI == EK_BIAS_SOFTPLUS) softplus100_fast16(v);
+#pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float x = v[j] + s_bias[c0 + j];
-            float y;
-            if constexpr (EPI == EK_BIAS_SOFTPLUS) y = softplus100_fast(x);
-            else if constexpr (EPI == EK_BIAS_RELU) y = fmaxf(x, 0.0f);
-            else y = apply_act(x, p.act, p.act_param);
+            float y = v[j];
+            if constexpr (EPI == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
+            else if constexpr (EPI == EK_BIAS_GENERIC) y = apply_act(y, p.act, p.act_param);
             r[j] = p.oscale * y;
           }
           store_block16(p.out + size_t(row0) * p.ldo + c0, p.ldo, rows_valid, nmain - c0, v_out, stg, lane, r);
@@ -147,10 +148,11 @@ __global__ void __launch_bounds__(kLinearThreads, 1) umma_linear_kernel(const Li
             for (int j = 0; j < 16; ++j) s[j] = 1.0f;
           } else {
             load_block16(p.H + size_t(row0) * p.ldh + c0, p.ldh, rows_valid, cm, vec_ok(p.H, p.ldh), stg, lane, s);
+            if constexpr (EPI == EK_DACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if constexpr (EPI == EK_DACT_RELU) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
-              else s[j] = dsoftplus100_from_h_fast(s[j] * p.hscale);
+              for (int j = 0; j < 16; ++j) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
+            } else {
+              dsoftplus100_from_h_fast16(s, p.hscale);
             }
           }
 #pragma unroll

@@ -28,6 +28,25 @@ __device__ __forceinline__ float dsoftplus100_from_h_fast(float h) {
   return z > 20.0f ? 1.0f : 1.0f - exp2f(-z * 1.4426950408889634f);
 }
 
+// batched versions over a 16-element register block: the three stages are written as separate loops so that the
+// sixteen MUFU chains are independent and issue back to back (ptxas otherwise serialises them through one register)
+__device__ __forceinline__ void softplus100_fast16(float* x) {
+  float t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = exp2f(fminf(100.0f * x[j], 20.0f) * 1.4426950408889634f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = __log2f(1.0f + t[j]);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = (100.0f * x[j] > 20.0f) ? x[j] : t[j] * (0.6931471805599453f * 0.01f);
+}
+__device__ __forceinline__ void dsoftplus100_from_h_fast16(float* h, float hscale) {
+  float t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = exp2f(-(100.0f * hscale * 1.4426950408889634f) * h[j]);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h[j] = (100.0f * hscale * h[j] > 20.0f) ? 1.0f : 1.0f - t[j];
+}
+
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
   const uint32_t hb = *reinterpret_cast<uint32_t*>(&h);
