@@ -20,6 +20,10 @@
 // next A operand from its own `save` buffer, where ray_fill / pe_tangent pre-stored PE/sqrt2 resp. its tangent.
 #include "umma_common.cuh"
 
+#ifndef NERO_EARLY_ISSUE
+#define NERO_EARLY_ISSUE 0   // issue all aux-operand loads of a block before reading the accumulator
+#endif
+
 namespace nero {
 
 constexpr int kMaxChainLayers = 10;
@@ -93,6 +97,15 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
     float r[16];
     if (b < nblk && c0 < L.ncol_out) {
       float v[16];
+      const int cm = nmain - c0;   // main columns in this block (may be <= 0)
+#if NERO_EARLY_ISSUE
+      float4 hraw[4], araw[4], vraw[4];
+      if constexpr (!kBias) {      // all aux loads of this block are in flight before the accumulator is read
+        if constexpr (KIND != EK_DACT_NONE) issue_block16(L.H + size_t(row0) * L.ldh + c0, L.ldh, rows_valid, cm, vec_ok(L.H, L.ldh), lane, hraw);
+        if (L.addend) issue_block16(L.addend + size_t(row0) * L.ldadd + c0, L.ldadd, rows_valid, cm, vec_ok(L.addend, L.ldadd), lane, araw);
+        if constexpr (KIND == EK_TANGENT) issue_block16(L.V + size_t(row0) * L.ldv + c0, L.ldv, rows_valid, cm, vec_ok(L.V, L.ldv), lane, vraw);
+      }
+#endif
       tmem_ld16(tmem_lane_base + kAccCol + c0, v);
       tmem_ld_wait();
       if constexpr (kBias) {
@@ -107,13 +120,16 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
           r[j] = L.oscale * y;
         }
       } else {
-        const int cm = nmain - c0;
         float s[16];
         if constexpr (KIND == EK_DACT_NONE) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) s[j] = 1.0f;
         } else {
+#if NERO_EARLY_ISSUE
+          finish_block16(hraw, stg, lane, s);
+#else
           load_block16(L.H + size_t(row0) * L.ldh + c0, L.ldh, rows_valid, cm, vec_ok(L.H, L.ldh), stg, lane, s);
+#endif
           if constexpr (KIND == EK_DACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
@@ -125,7 +141,11 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
         for (int j = 0; j < 16; ++j) r[j] = L.oscale * s[j] * v[j];
         if (L.addend) {
           float a[16];
+#if NERO_EARLY_ISSUE
+          finish_block16(araw, stg, lane, a);
+#else
           load_block16(L.addend + size_t(row0) * L.ldadd + c0, L.ldadd, rows_valid, cm, vec_ok(L.addend, L.ldadd), stg, lane, a);
+#endif
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] += a[j];
         }
@@ -138,9 +158,13 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
               L.tail[size_t(row0 + lane) * L.ldt + (c0 + j - L.ncol_main)] = L.oscale * v[j];
         }
         if constexpr (KIND == EK_TANGENT) {
+          float vv[16];
+#if NERO_EARLY_ISSUE
+          finish_block16(vraw, stg, lane, vv);
+#else
+          load_block16(L.V + size_t(row0) * L.ldv + c0, L.ldv, rows_valid, cm, vec_ok(L.V, L.ldv), stg, lane, vv);
+#endif
           if (cm > 0) {
-            float vv[16];
-            load_block16(L.V + size_t(row0) * L.ldv + c0, L.ldv, rows_valid, cm, vec_ok(L.V, L.ldv), stg, lane, vv);
 #pragma unroll
             for (int j = 0; j < 16; ++j) vv[j] = 100.0f * (1.0f - s[j]) * vv[j] * v[j];
             store_block16(L.out2 + size_t(row0) * L.ldo2 + c0, L.ldo2, rows_valid, cm, vec_ok(L.out2, L.ldo2), stg, lane, vv);

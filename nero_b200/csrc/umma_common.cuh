@@ -30,21 +30,31 @@ __device__ __forceinline__ float dsoftplus100_from_h_fast(float h) {
 
 // batched versions over a 16-element register block: the three stages are written as separate loops so that the
 // sixteen MUFU chains are independent and issue back to back (ptxas otherwise serialises them through one register)
+__device__ __forceinline__ float ex2_ftz(float x) {   // MUFU.EX2 without the denormal-range fix-up of exp2f()
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void softplus100_fast16(float* x) {
   float t[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) t[j] = exp2f(fminf(100.0f * x[j], 20.0f) * 1.4426950408889634f);
+  for (int j = 0; j < 16; ++j) t[j] = ex2_ftz(fminf(x[j], 0.2f) * (100.0f * 1.4426950408889634f));
 #pragma unroll
-  for (int j = 0; j < 16; ++j) t[j] = __log2f(1.0f + t[j]);
+  for (int j = 0; j < 16; ++j) t[j] = lg2_ftz(1.0f + t[j]);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = (100.0f * x[j] > 20.0f) ? x[j] : t[j] * (0.6931471805599453f * 0.01f);
+  for (int j = 0; j < 16; ++j) x[j] = (x[j] > 0.2f) ? x[j] : t[j] * (0.6931471805599453f * 0.01f);
 }
+// sigma(100 a) from h = softplus(a) (possibly stored scaled by 1/hscale): 1 - 2^(-100*log2e*hscale*h); for
+// 100*hscale*h > 20 the exponential is < 2.1e-9, below fp32 resolution of 1 - t, so no branch is needed
 __device__ __forceinline__ void dsoftplus100_from_h_fast16(float* h, float hscale) {
-  float t[16];
+  const float k = -(100.0f * 1.4426950408889634f) * hscale;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) t[j] = exp2f(-(100.0f * hscale * 1.4426950408889634f) * h[j]);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) h[j] = (100.0f * hscale * h[j] > 20.0f) ? 1.0f : 1.0f - t[j];
+  for (int j = 0; j < 16; ++j) h[j] = 1.0f - ex2_ftz(k * h[j]);
 }
 
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {

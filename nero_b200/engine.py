@@ -374,6 +374,19 @@ class NerfNet:
     def forward(self, w, m_ptr, m_cap):
         kw = dict(m_ptr=m_ptr, m_cap=m_cap)
         N = w['NH']
+        if USE_CHAIN:
+            chain(Mat(w['XN']), self.P[0].k_valid,
+                  [CL(self.P[0], EK_BIAS_RELU, 256, save=Mat(N[1])), CL(self.P[1], EK_BIAS_RELU, 256, save=Mat(N[2])),
+                   CL(self.P[2], EK_BIAS_RELU, 256, save=Mat(N[3])), CL(self.P[3], EK_BIAS_RELU, 256, save=Mat(N[4])),
+                   CL(self.P[4], EK_BIAS_RELU, 256, save=Mat(w['H5'], 84), write_a=False)], m_ptr, m_cap, tag='nerf_fwd_a')
+            linear(Mat(w['H5']), self.P[5], Mat(N[6]), 256, act=ACT_RELU, **kw)     # K = 340 > 256: not chainable
+            chain(Mat(N[6]), 256,
+                  [CL(self.P[6], EK_BIAS_RELU, 256, save=Mat(N[7])), CL(self.P[7], EK_BIAS_RELU, 256, save=Mat(N[8])),
+                   CL(self.alpha, EK_BIAS_GENERIC, 1, save=Mat(w['DENS']), write_a=False),
+                   CL(self.feature, EK_BIAS_GENERIC, 256, save=Mat(w['FV']), write_a=False)], m_ptr, m_cap, tag='nerf_fwd_b')
+            linear(Mat(w['FV']), self.views, Mat(w['HV']), 128, act=ACT_RELU, **kw)
+            linear(Mat(w['HV']), self.rgb, Mat(w['RGBRAW']), 3, **kw)
+            return
         linear(Mat(w['XN']), self.P[0], Mat(N[1]), 256, act=ACT_RELU, **kw)
         linear(Mat(N[1]), self.P[1], Mat(N[2]), 256, act=ACT_RELU, **kw)
         linear(Mat(N[2]), self.P[2], Mat(N[3]), 256, act=ACT_RELU, **kw)
@@ -402,6 +415,25 @@ class NerfNet:
         wgrad(ws, Mat(w['dFV']), 256, Mat(N[8]), 256, self.feature, *gp(n.feature_linear), **kw)
         wgrad(ws, Mat(w['dDENS']), 1, Mat(N[8]), 256, self.alpha, *gp(n.alpha_linear), **kw)
         pl = n.pts_linears
+        if USE_CHAIN:
+            G = w['dNG']   # pre-activation gradients of layers 6..0 (dA holds layer 7's)
+            chain(Mat(dA), 256,
+                  [CL(self.P[7], EK_DACT_RELU, 256, transposed=True, H=Mat(N[7]), save=Mat(G[6])),
+                   CL(self.P[6], EK_DACT_RELU, 256, transposed=True, H=Mat(N[6]), save=Mat(G[5])),
+                   CL(self.P[5], EK_DACT_RELU, 256, transposed=True, H=Mat(w['H5'], 84), save=Mat(G[4])),
+                   CL(self.P[4], EK_DACT_RELU, 256, transposed=True, H=Mat(N[4]), save=Mat(G[3])),
+                   CL(self.P[3], EK_DACT_RELU, 256, transposed=True, H=Mat(N[3]), save=Mat(G[2])),
+                   CL(self.P[2], EK_DACT_RELU, 256, transposed=True, H=Mat(N[2]), save=Mat(G[1])),
+                   CL(self.P[1], EK_DACT_RELU, 256, transposed=True, H=Mat(N[1]), save=Mat(G[0]))], m_ptr, m_cap, tag='nerf_bwd')
+            wgrad(ws, Mat(dA), 256, Mat(N[7]), 256, self.P[7], *gp(pl[7]), **kw)
+            wgrad(ws, Mat(G[6]), 256, Mat(N[6]), 256, self.P[6], *gp(pl[6]), **kw)
+            wgrad(ws, Mat(G[5]), 256, Mat(w['H5']), self.P[5].k_valid, self.P[5], *gp(pl[5]), **kw)
+            wgrad(ws, Mat(G[4]), 256, Mat(N[4]), 256, self.P[4], *gp(pl[4]), **kw)
+            wgrad(ws, Mat(G[3]), 256, Mat(N[3]), 256, self.P[3], *gp(pl[3]), **kw)
+            wgrad(ws, Mat(G[2]), 256, Mat(N[2]), 256, self.P[2], *gp(pl[2]), **kw)
+            wgrad(ws, Mat(G[1]), 256, Mat(N[1]), 256, self.P[1], *gp(pl[1]), **kw)
+            wgrad(ws, Mat(G[0]), 256, Mat(w['XN']), self.P[0].k_valid, self.P[0], *gp(pl[0]), **kw)
+            return
         linear(Mat(dA), self.P[7], Mat(dB), 256, H=Mat(N[7]), **R, **kw)
         wgrad(ws, Mat(dA), 256, Mat(N[7]), 256, self.P[7], *gp(pl[7]), **kw)
         linear(Mat(dB), self.P[6], Mat(dA), 256, H=Mat(N[6]), **R, **kw)
@@ -550,6 +582,7 @@ class ShapeEngine:
         w['ABAR'] = [z(cap, 256) for _ in range(8)]
         w.update(dALPHA_OUT=z(cap), dCOLOR_OUT=z(cap, 4), dDENS=z(cap, 4), dRGBRAW=z(cap, 4), dHV=z(cap, 128), dFV=z(cap, 256),
                  dNa=z(cap, 256), dNb=z(cap, 256))
+        w['dNG'] = [z(cap, 256) for _ in range(7)]
         self.bw_ready = True
 
     # ------------------------------------------------------------------ sampling (renderer.py:403-443)
