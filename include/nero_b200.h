@@ -110,6 +110,11 @@ int nero_reg_prepare(const float* rays_o, const float* rays_d, const float* z_va
 int nero_reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
                   float* X0, int ldx, float* H4, int ldh, void* stream);
 
+/* arbitrary query points (validation render network/renderer.py:465-482; grid query network/field.py:1090-1117 via
+ * sdf_network.sdf, extract_mesh.py:27): PE rows into X0 and the layer-4 skip tail; optionally PTS, identity ray ids and
+ * xyz into Y8 (each may be NULL) */
+int nero_points_fill(const float* pts3, int N, float* pts, int* ray_in, float* X0, int ldx, float* Y8, int ldy, float* H4, int ldh, void* stream);
+
 /* ---- analytic SDF gradient helpers (SDFNetwork.gradient, network/field.py:155-167) ------------------------- */
 int nero_dact_times_row(const float* H, int ldh, const float* row, float* V, int ldv, int ncol, const int* m_ptr, int m_cap, void* stream);
 int nero_pe_grad(const float* X0, int ldx, const float* U0, int ldu, const float* US, int lds, float* G, const int* m_ptr, int m_cap, void* stream);

@@ -121,6 +121,7 @@ int reg_prepare(const float* rays_o, const float* rays_d, const float* z_vals, i
                 int* off, int* off_dummy, int* n, int* n_dummy, cudaStream_t st);
 int reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
              float* X0, int ldx, float* H4, int ldh, cudaStream_t st);
+int points_fill(const float* pts3, int N, float* pts, int* ray_in, float* X0, int ldx, float* Y8, int ldy, float* H4, int ldh, cudaStream_t st);
 struct ChainParams;
 int chain_dispatch(const ChainParams& p, cudaStream_t stream);
 int occ_loss(const float* occ_prob, const float* gt, const int* sel, const int* p_ptr, int p_cap, float* loss_sum, float* docc_sign,
@@ -186,6 +187,9 @@ int nero_reg_prepare(const float* rays_o, const float* rays_d, const float* z_va
 int nero_reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int R, int S, float radius, const int* off, float* pts,
                   float* X0, int ldx, float* H4, int ldh, void* stream) {
   return reg_fill(rays_o, rays_d, z_vals, R, S, radius, off, pts, X0, ldx, H4, ldh, (cudaStream_t)stream);
+}
+int nero_points_fill(const float* pts3, int N, float* pts, int* ray_in, float* X0, int ldx, float* Y8, int ldy, float* H4, int ldh, void* stream) {
+  return points_fill(pts3, N, pts, ray_in, X0, ldx, Y8, ldy, H4, ldh, (cudaStream_t)stream);
 }
 int nero_row_axpy(const float* a, int lda, const float* X, int ldx, float* Y, int ldy, int ncol, const int* m_ptr, int m_cap, void* stream) {
   return row_axpy(a, lda, X, ldx, Y, ldy, ncol, m_ptr, m_cap, (cudaStream_t)stream);

@@ -200,6 +200,20 @@ __global__ void reg_fill_kernel(const float* __restrict__ rays_o, const float* _
   }
 }
 
+// arbitrary query points (validation render, renderer.py:465-482): PTS / identity ray ids / PE rows / xyz for the material input
+__global__ void points_fill_kernel(const float* __restrict__ pts3, int N, float* pts, int* ray_in, float* X0, int ldx, float* Y8,
+                                   int ldy, float* H4, int ldh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float p[3] = {pts3[i * 3], pts3[i * 3 + 1], pts3[i * 3 + 2]};
+  if (pts) *reinterpret_cast<float4*>(pts + size_t(i) * 4) = make_float4(p[0], p[1], p[2], 0.f);
+  if (ray_in) ray_in[i] = i;
+  float pe[39];
+  pe_encode<3>(p, 6, pe);
+  for (int c = 0; c < 39; ++c) { X0[size_t(i) * ldx + c] = pe[c]; H4[size_t(i) * ldh + 217 + c] = pe[c] * kInvSqrt2; }
+  if (Y8) { Y8[size_t(i) * ldy + 256] = p[0]; Y8[size_t(i) * ldy + 257] = p[1]; Y8[size_t(i) * ldy + 258] = p[2]; }
+}
+
 // ------------------------------------------------------------------ SDF-gradient sweep ends
 // V[i,j] = softplus'(a)(from H) * row[j]      (first step of the reverse sweep: v_7 = sigma_7 * W_8[0,:])
 __global__ void dact_times_row_kernel(const float* __restrict__ H, int ldh, const float* __restrict__ row, float* V, int ldv,
@@ -419,6 +433,12 @@ int reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int 
              float* X0, int ldx, float* H4, int ldh, cudaStream_t st) {
   if (R <= 0) return NERO_OK;
   reg_fill_kernel<<<blocks_for(long(R) * 32, 128), 128, 0, st>>>(rays_o, rays_d, z_vals, R, S, radius, off, pts, X0, ldx, H4, ldh);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+int points_fill(const float* pts3, int N, float* pts, int* ray_in, float* X0, int ldx, float* Y8, int ldy, float* H4, int ldh, cudaStream_t st) {
+  if (N <= 0) return NERO_OK;
+  points_fill_kernel<<<blocks_for(N, 128), 128, 0, st>>>(pts3, N, pts, ray_in, X0, ldx, Y8, ldy, H4, ldh);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

@@ -67,6 +67,24 @@ def upload_ide_table():
         _ide_uploaded = True
 
 
+def _linear_to_srgb_torch(x):
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.0031308, 323 / 25 * x, (211 * torch.clamp(x, min=eps) ** (5 / 12) - 11) / 200)
+
+
+def _fg_lookup_torch(lut, uv):
+    """bilinear clamp lookup of the [256,256,2] LUT (validation path only; the training path does this in shade_combine)."""
+    H, W = lut.shape[0], lut.shape[1]
+    fx, fy = uv[:, 0] * W - 0.5, uv[:, 1] * H - 0.5
+    x0f, y0f = torch.floor(fx), torch.floor(fy)
+    tx, ty = (fx - x0f)[:, None], (fy - y0f)[:, None]
+    x0, x1 = x0f.long().clamp(0, W - 1), (x0f.long() + 1).clamp(0, W - 1)
+    y0, y1 = y0f.long().clamp(0, H - 1), (y0f.long() + 1).clamp(0, H - 1)
+    a = lut[y0, x0] * (1 - tx) + lut[y0, x1] * tx
+    b = lut[y1, x0] * (1 - tx) + lut[y1, x1] * tx
+    return a * (1 - ty) + b * ty
+
+
 class Grads:
     """Maps parameters to their .grad buffers; missing grads become views of ONE flat zeroed buffer (the buffer a
     data-parallel run all-reduces with a single NCCL call)."""
@@ -633,23 +651,7 @@ class ShapeEngine:
         n_in, n_out = w['n_in'], w['n_out']
         # ---- inner samples: SDF value + analytic gradient
         self.sdf.forward_with_gradient(w, n_in, cap)
-        # ---- materials
-        A = w['ACT']
-        matin = Mat(w['Y8'])
-        self.m_met.forward(matin, A['met'], Mat(w['OUTS'], O_MET), n_in, cap)
-        self.m_rough.forward(matin, A['rough'], Mat(w['OUTS'], O_ROUGH), n_in, cap)
-        self.m_alb.forward(matin, A['alb'], Mat(w['OUTS'], O_ALB), n_in, cap)
-        hp = human_poses.contiguous() if self.human else None
-        K('nero_shade_prep_fwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['E'], E_LD, w['GEO'], hp, w['EH'] if self.human else None,
-          64, 8, n_in, cap)
-        self.m_outer.forward(Mat(w['E'], E_IDER), A['odir'], Mat(w['OUTS'], O_LDIR), n_in, cap)
-        self.m_outer.forward(Mat(w['E'], E_IDEN), A['odif'], Mat(w['OUTS'], O_LD), n_in, cap)
-        self.m_inner.forward(Mat(w['E'], E_PE8X), A['inner'], Mat(w['OUTS'], O_LI), n_in, cap)
-        self.m_iw.forward(Mat(w['E'], 0), A['iw'], Mat(w['OUTS'], O_IW), n_in, cap)
-        if self.human:
-            self.m_human.forward(Mat(w['EH']), A['human'], Mat(w['OUTS'], O_HUM), n_in, cap)
-        K('nero_shade_combine_fwd', w['OUTS'], w['GEO'], self.lut, self.exp_max, 1 if self.human else 0, w['COLOR_IN'], w['OCCP'], w['REFL'],
-          n_in, cap)
+        self._shade_forward(rays_d, human_poses, n_in, cap)
         K('nero_sdf_alpha_fwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, float(cos_anneal_ratio), w['ALPHA_IN'],
           w['GERR'], n_in, cap)
         # ---- outer samples: NeRF++
@@ -678,7 +680,7 @@ class ShapeEngine:
         self.n_reg = counts[2] if with_reg else 0
         if occ_on:
             P = self._occ_forward(counts[1], perm)
-        self.state = dict(R=R, S=S, N_in=N_in, P=P, rays_d=rays_d, hp=hp, car=float(cos_anneal_ratio), step=step)
+        self.state = dict(R=R, S=S, N_in=N_in, P=P, rays_d=rays_d, hp=self._hp, car=float(cos_anneal_ratio), step=step)
         return rgb, N_in, P
 
     def _occ_forward(self, cnt, perm):
@@ -707,6 +709,118 @@ class ShapeEngine:
         K('nero_occ_loss', w['OCCP'], w['OCC_GT'], sel, None, P, w['OCC_LOSS'], w['DOCC'])
         self.occ_sel = sel
         return P
+
+    def _shade_forward(self, rays_d, human_poses, n_in, cap):
+        """AppShadingNetwork.forward on the compacted inner samples (network/field.py:591-651)."""
+        w = self.w
+        # ---- materials
+        A = w['ACT']
+        matin = Mat(w['Y8'])
+        self.m_met.forward(matin, A['met'], Mat(w['OUTS'], O_MET), n_in, cap)
+        self.m_rough.forward(matin, A['rough'], Mat(w['OUTS'], O_ROUGH), n_in, cap)
+        self.m_alb.forward(matin, A['alb'], Mat(w['OUTS'], O_ALB), n_in, cap)
+        hp = human_poses.contiguous() if self.human else None
+        self._hp = hp
+        K('nero_shade_prep_fwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['E'], E_LD, w['GEO'], hp, w['EH'] if self.human else None,
+          64, 8, n_in, cap)
+        self.m_outer.forward(Mat(w['E'], E_IDER), A['odir'], Mat(w['OUTS'], O_LDIR), n_in, cap)
+        self.m_outer.forward(Mat(w['E'], E_IDEN), A['odif'], Mat(w['OUTS'], O_LD), n_in, cap)
+        self.m_inner.forward(Mat(w['E'], E_PE8X), A['inner'], Mat(w['OUTS'], O_LI), n_in, cap)
+        self.m_iw.forward(Mat(w['E'], 0), A['iw'], Mat(w['OUTS'], O_IW), n_in, cap)
+        if self.human:
+            self.m_human.forward(Mat(w['EH']), A['human'], Mat(w['OUTS'], O_HUM), n_in, cap)
+        K('nero_shade_combine_fwd', w['OUTS'], w['GEO'], self.lut, self.exp_max, 1 if self.human else 0, w['COLOR_IN'], w['OCCP'], w['REFL'],
+          n_in, cap)
+
+    # ------------------------------------------------------------------ SDF grid query (field.py:150-153 via extract_mesh.py:27)
+    QUERY_CHUNK = 131072
+
+    def sdf_query(self, x):
+        """sdf_network.sdf(x): value-only SDF of arbitrary points, forward only, chunked through a private workspace."""
+        shape = x.shape[:-1]
+        x = x.reshape(-1, 3).to(self.dev, torch.float32).contiguous()
+        M = x.shape[0]
+        out = torch.empty(M, 1, device=self.dev)
+        if M == 0:
+            return out.reshape(*shape, 1)
+        q = getattr(self, '_qws', None)
+        if q is None:
+            c = self.QUERY_CHUNK
+            z = lambda *s: torch.zeros(*s, device=self.dev)
+            q = self._qws = dict(X0=z(c, 64), SA=z(c, 256), SB=z(c, 256), SC=z(c, 256), OUT=z(c, 1))
+        self.sdf.prep()
+        for c0 in range(0, M, self.QUERY_CHUNK):
+            n = min(self.QUERY_CHUNK, M - c0)
+            K('nero_points_fill', x[c0:c0 + n], n, None, None, q['X0'], 64, None, 0, q['SC'], 256)
+            self.sdf.sdf_only(q['X0'], q['SA'], q['SB'], q['SC'], q['OUT'], None, n)
+            out[c0:c0 + n] = q['OUT'][:n]
+        return out.reshape(*shape, 1)
+
+    # ------------------------------------------------------------------ validation extras (renderer.py:465-482)
+    def validation_info(self, rays_o, rays_d, z_vals, human_poses):
+        """depth, normal, shading intermediates and occ_prob_gt on the expected surface point of every ray.
+        Forward only (called under no_grad); re-uses the training workspaces."""
+        R, S = z_vals.shape
+        w, dev = self.w, self.dev
+        weights = torch.empty(R, S, device=dev)
+        rgb = torch.empty(R, 3, device=dev)
+        K('nero_composite_fwd', w['slot'], R, S, w['ALPHA_IN'], w['COLOR_IN'], w['ALPHA_OUT'], w['COLOR_OUT'], rgb, weights)
+        depth = torch.sum(weights * z_vals, -1, keepdim=True)
+        points = (depth * rays_d + rays_o).contiguous()
+        K('nero_points_fill', points, R, w['PTS'], w['RAY_IN'], w['X0'], 64, w['Y8'], Y8_LD, w['H'][4], 256)
+        self.sdf.forward_with_gradient(w, None, R)
+        self._shade_forward(rays_d, human_poses, None, R)
+        O = w['OUTS'][:R]
+        geo = w['GEO'][:R]
+        grads = w['G'][:R, :3]
+        inner = (torch.norm(points, dim=-1, keepdim=True) <= 1.0).float()
+        met, rough, alb = O[:, O_MET:O_MET + 1], O[:, O_ROUGH:O_ROUGH + 1], O[:, O_ALB:O_ALB + 3]
+        Ld, Ldir, Li, iw = O[:, O_LD:O_LD + 3], O[:, O_LDIR:O_LDIR + 3], O[:, O_LI:O_LI + 3], O[:, O_IW:O_IW + 1]
+        occ = iw * 0.5 + 0.5
+        occ_ = occ.clamp(0, 1)
+        if self.human:
+            hit = geo[:, 7:8]
+            hl = O[:, O_HUM:O_HUM + 4] * hit
+            Lh, wh = hl[:, :3], hl[:, 3:].clamp(0, 1)
+        else:
+            Lh, wh = 0.0, 0.0
+        spec_light = Li * occ_ + (Lh * wh + Ldir * (1 - wh)) * (1 - occ_)
+        uv = torch.cat([geo[:, 3:4].clamp(0, 1), rough.clamp(0, 1)], -1)
+        fg = _fg_lookup_torch(self.lut[0], uv)
+        diff_alb = (1 - met) * alb
+        spec_alb = 0.04 * (1 - met) + met * alb
+        spec_ref = spec_alb * fg[:, 0:1] + fg[:, 1:2]
+        srgb = _linear_to_srgb_torch
+        out = {'depth': depth, 'normal': ((torch.nn.functional.normalize(grads, dim=-1) + 1.0) * 0.5) * inner}
+        inter = {'specular_albedo': spec_alb, 'specular_ref': spec_ref.clamp(0, 1), 'specular_light': srgb(spec_light).clamp(0, 1),
+                 'specular_color': srgb(spec_ref * spec_light).clamp(0, 1), 'diffuse_albedo': diff_alb,
+                 'diffuse_light': srgb(Ld).clamp(0, 1), 'diffuse_color': srgb(diff_alb * Ld).clamp(0, 1), 'metallic': met.clone(),
+                 'roughness': rough.clone(), 'occ_prob': occ.clamp(0, 1), 'indirect_light': Li * occ_}
+        if self.human:
+            inter['human_light'] = srgb(Lh * wh)
+        # occlusion ground truth: get_intersection(points, reflective, sn0=128, sn1=9) (field.py:454-484)
+        sel = torch.nonzero(torch.norm(points, dim=-1) < 0.999)[:, 0].to(torch.int32).contiguous()
+        P = int(sel.shape[0])
+        gt = torch.zeros(R, 1, device=dev)
+        if P > 0:
+            var = self.p.deviation_network.variance.detach()
+            if not hasattr(self, 't_lin128'):
+                self.t_lin128 = torch.linspace(0, 1, 128).to(dev)
+            chunk = w['SX0'].shape[0] // 128          # points per pass through the sampling workspace
+            oo, dd = torch.empty(chunk, 3, device=dev), torch.empty(chunk, 3, device=dev)
+            zz, nz, g_ = torch.empty(chunk, 128, device=dev), torch.empty(chunk, 16, device=dev), torch.empty(chunk, device=dev)
+            for c0 in range(0, P, chunk):
+                sl = sel[c0:c0 + chunk]
+                pc = int(sl.shape[0])
+                K('nero_occ_init', w['PTS'], w['REFL'], sl, None, pc, 128, self.t_lin128, oo, dd, zz, 128, w['SX0'], 64, w['SC'], 256)
+                self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, pc * 128)
+                K('nero_upsample', oo, dd, pc, zz, 128, w['SSDF'], 128, 128, 9, var, 3.0e38, 1, 1, nz, 16, w['SX0'], 64, w['SC'], 256, None)
+                self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, pc * 9)
+                K('nero_upsample', oo, dd, pc, nz, 16, w['SSDF'], 9, 9, 9, var, 3.0e38, 1, 1, None, 0, None, 0, None, 0, g_)
+                gt[sl.long(), 0] = g_[:pc]
+        out['occ_prob_gt'] = gt
+        out.update({k: v * inner for k, v in inter.items()})
+        return out
 
     # ------------------------------------------------------------------ render_core backward
     def render_core_backward(self, d_rgb, d_gerr, d_occ_scale):

@@ -70,9 +70,15 @@ class NeROShapeRenderer(nn.Module):
             self.outer_nerf.rgb_linear.bias.fill_(float(np.log(0.5)))
         self.color_network = ShadingParams(c['shader_config'])
         self._engine = None
+        # extract_mesh.py:27 calls network.sdf_network.sdf(x): route it to the forward-only CUDA chain
+        self.sdf_network.sdf = self._sdf_query
         self._weights_dirty = True
         if training:
             self._init_dataset()
+
+    def _sdf_query(self, x):
+        with torch.no_grad():
+            return self.engine.sdf_query(x)
 
     # ------------------------------------------------------------------ engine plumbing
     @property
@@ -146,8 +152,6 @@ class NeROShapeRenderer(nn.Module):
                                 None if rand_bg is None else rand_bg.contiguous())
 
     def render_core(self, rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio=0.0, step=None, is_train=True, perm=None):
-        if not is_train:
-            raise NotImplementedError('validation render (compute_validation_info) is not part of the B200 hot path yet')
         e = self.engine
         if not getattr(self, '_weights_fresh', False):
             e.prepare_weights()          # render_core called on its own: fold weight-norm / rebuild operand images
@@ -165,6 +169,9 @@ class NeROShapeRenderer(nn.Module):
             outputs['sdf_vals'] = sdf_vals
         if self.cfg['apply_occ_loss']:
             outputs['loss_occ'] = loss_occ
+        if not is_train:      # network/renderer.py:602-604 -> compute_validation_info (:465-482)
+            with torch.no_grad():
+                outputs.update(e.validation_info(rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous(), human_poses.contiguous()))
         return outputs
 
     def render(self, rays_o, rays_d, near, far, human_poses, perturb_overwrite=-1, cos_anneal_ratio=0.0, is_train=True, step=None):
@@ -233,9 +240,53 @@ class NeROShapeRenderer(nn.Module):
         outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], batch['rgbs'])
         return outputs
 
+    def test_step(self, index, step):
+        """Full-image validation render in chunks of `test_ray_num` rays (network/renderer.py:274-316).  Needs the host
+        repo's `dataset` package (database access) exactly like the reference; the per-chunk render runs on the CUDA path."""
+        import cv2
+        from network.renderer import imgs_info_slice, imgs_info_downsample     # host repo helpers (pure tensor slicing)
+        imgs_info = imgs_info_slice(self.test_imgs_info, torch.from_numpy(np.asarray([index], np.int64)))
+        gt_depth, gt_mask = self.database.get_depth(self.test_ids[index])
+        if self.cfg['test_downsample_ratio']:
+            imgs_info = imgs_info_downsample(imgs_info, self.cfg['downsample_ratio'])
+            h, w = gt_depth.shape
+            dh, dw = int(self.cfg['downsample_ratio'] * h), int(self.cfg['downsample_ratio'] * w)
+            gt_depth = cv2.resize(gt_depth, (dw, dh), interpolation=cv2.INTER_NEAREST)
+            gt_mask = cv2.resize(gt_mask.astype(np.uint8), (dw, dh), interpolation=cv2.INTER_NEAREST)
+        gt_depth, gt_mask = torch.from_numpy(gt_depth), torch.from_numpy(gt_mask.astype(np.int32))
+        ray_batch, poses, rn, h, w = self._construct_ray_batch(imgs_info)
+        return self.render_image(ray_batch, poses.float(), h, w, step, gt_depth, gt_mask)
+
+    def render_image(self, ray_batch, poses, h, w, step, gt_depth=None, gt_mask=None):
+        """The chunk loop of test_step (network/renderer.py:289-316) on an already constructed ray batch."""
+        dev = self.deviation_network.variance.device
+        poses = poses.to(dev)
+        ray_batch = {k: v.to(dev) for k, v in ray_batch.items()}
+        rn, trn = ray_batch['dirs'].shape[0], self.cfg['test_ray_num']
+        keys = ['ray_rgb', 'gradient_error', 'normal', 'depth', 'diffuse_albedo', 'diffuse_light', 'diffuse_color', 'specular_albedo',
+                'specular_light', 'specular_color', 'specular_ref', 'metallic', 'roughness', 'occ_prob', 'indirect_light', 'occ_prob_gt']
+        if self.cfg['shader_config'].get('human_light', False) or self.engine.human:
+            keys.append('human_light')
+        outputs = {k: [] for k in keys}
+        with torch.no_grad():
+            for ri in range(0, rn, trn):
+                cur = {k: v[ri:ri + trn] for k, v in ray_batch.items()}
+                rays_o, rays_d, near, far, human_poses = self._process_ray_batch(cur, poses)
+                o = self.render(rays_o, rays_d, near, far, human_poses, 0, 0, is_train=False, step=step)
+                for k in keys:
+                    outputs[k].append(o[k].detach())
+        outputs = {k: torch.cat(v, 0) for k, v in outputs.items()}
+        outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], ray_batch['rgbs'])
+        outputs['gt_rgb'] = ray_batch['rgbs'].reshape(h, w, 3)
+        outputs['ray_rgb'] = outputs['ray_rgb'].reshape(h, w, 3)
+        if gt_depth is not None:
+            outputs['gt_depth'], outputs['gt_mask'] = gt_depth.unsqueeze(-1), gt_mask.unsqueeze(-1)
+        self.zero_grad()
+        return outputs
+
     def forward(self, data):
-        if 'eval' in data:
-            raise NotImplementedError('validation render is outside the B200 hot path (SURVEY.md section 8f item 3)')
+        if 'eval' in data:        # network/renderer.py:319-330
+            return self.test_step(int(data['index']) if not isinstance(data['index'], int) else data['index'], step=data['step'])
         return self.train_step(data['step'])
 
 

@@ -122,6 +122,25 @@ def make_shape_fixture(name, cfg, R, steps, seed=6033, pseed=7):
           'occ', {s: float(out[f's{s}_loss_occ'].mean()) for s in steps})
 
 
+def make_validation_fixture(name, cfg, R, step, seed=6033, pseed=7):
+    """is_train=False render (network/renderer.py:465-482, 602-604): depth / normal / shading intermediates /
+    occ_prob_gt on the expected surface points."""
+    net = ref_shim.build_reference_shape_renderer(cfg, seed=seed)
+    sd = O.perturb_params({k: v.detach().clone() for k, v in net.state_dict().items()}, seed=pseed)
+    net.load_state_dict(sd)
+    rays = O.synthetic_rays(R, seed=seed)
+    c = O.merged_cfg(cfg)
+    with torch.no_grad():
+        z = net.sample_ray(rays['rays_o'], rays['rays_d'], rays['near'], rays['far'], 0)
+    o = net.render_core(rays['rays_o'], rays['rays_d'], z, rays['human_poses'], cos_anneal_ratio=O.get_anneal_val(c, step),
+                        step=step, is_train=False)
+    out = {'param_checksums': param_checksums(sd), 'R': R, 'seed': seed, 'pseed': pseed, 'step': step, 'z_vals': z}
+    out.update({'val_' + k: v for k, v in o.items()})
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **npy(out))
+    print(name, 'saved;', sorted(o.keys()), 'inner', float((o['normal'].abs().sum(-1) > 0).float().mean()),
+          'occ_gt mean', float(o['occ_prob_gt'].mean()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     make_encoding_kats()
@@ -129,7 +148,14 @@ def main():
     make_shape_fixture('shape_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}},
                        24, [500, 30000])
     make_shape_fixture('shape_bell_full_r16', {}, 16, [30000])
+    make_validation_fixture('shape_val_bell_r32', {'n_samples': 32, 'n_importance': 32}, 32, 30000)
+    make_validation_fixture('shape_val_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}}, 24, 30000)
 
 
 if __name__ == '__main__':
-    main()
+    if '--val-only' in sys.argv:
+        ref_shim.install()
+        make_validation_fixture('shape_val_bell_r32', {'n_samples': 32, 'n_importance': 32}, 32, 30000)
+        make_validation_fixture('shape_val_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}}, 24, 30000)
+    else:
+        main()

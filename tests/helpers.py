@@ -40,3 +40,4 @@ FIXTURE_CFGS = {
     'shape_bell_full_r16': {},
 }
 FIXTURE_STEPS = {'shape_bell_r32': [500, 10000, 30000], 'shape_bear_r24': [500, 30000], 'shape_bell_full_r16': [30000]}
+VAL_FIXTURES = {'shape_val_bell_r32': FIXTURE_CFGS['shape_bell_r32'], 'shape_val_bear_r24': FIXTURE_CFGS['shape_bear_r24']}

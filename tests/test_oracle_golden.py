@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import nero_oracle as O
-from helpers import load_golden, build_params, param_checksums, t, rays_from_golden, FIXTURE_CFGS, FIXTURE_STEPS
+from helpers import load_golden, build_params, param_checksums, t, rays_from_golden, FIXTURE_CFGS, FIXTURE_STEPS, VAL_FIXTURES
 
 
 def test_encoding_kats():
@@ -68,3 +68,22 @@ def test_shape_fixture(name):
         for k in g:
             if k.startswith(pre + 'grad::'):
                 np.testing.assert_allclose(p[k.split('::')[1]].grad.numpy(), g[k], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', list(VAL_FIXTURES))
+def test_validation_fixture(name):
+    """is_train=False render (network/renderer.py:465-482) of the oracle vs the unmodified reference."""
+    g = load_golden(name)
+    cfg = VAL_FIXTURES[name]
+    sd = build_params(cfg, int(g['seed']), int(g['pseed']))
+    np.testing.assert_allclose(param_checksums(sd), g['param_checksums'], rtol=1e-12)
+    rays = O.synthetic_rays(int(g['R']), seed=int(g['seed']))
+    c = O.merged_cfg(cfg)
+    step = int(g['step'])
+    with torch.no_grad():
+        out = O.render_core(sd, c, sd['color_network.FG_LUT'][0], rays['rays_o'], rays['rays_d'], t(g['z_vals']), rays['human_poses'],
+                            O.get_anneal_val(c, step), step, is_train=False)
+    keys = [k[4:] for k in g if k.startswith('val_')]
+    assert set(keys) == set(out.keys())
+    for k in keys:
+        np.testing.assert_allclose(out[k].numpy().reshape(-1), g['val_' + k].reshape(-1), rtol=2e-5, atol=2e-6, err_msg=k)

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 import nero_oracle as O
-from helpers import load_golden, build_params, t, rays_from_golden, FIXTURE_CFGS, FIXTURE_STEPS
+from helpers import load_golden, build_params, t, rays_from_golden, FIXTURE_CFGS, FIXTURE_STEPS, VAL_FIXTURES
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -51,7 +51,8 @@ def test_sampling_matches_reference(name):
         # inverse-CDF sampling amplifies the ~1e-5 SDF differences of the split-bf16 MLP where a bin holds ~1e-5 of the
         # mass (the fp32 reference itself moves by up to 6e-4 when its BLAS blocking changes): quantile criteria
         frac4, frac3 = np.mean(d[:, :n_in] < 1e-4), np.mean(d[:, :n_in] < 1e-3)
-        assert frac4 > 0.90 and frac3 > 0.995 and d[:, :n_in].max() < 5e-3, (frac4, frac3, d[:, :n_in].max())
+        # a sample whose u lands on a CDF step can move by up to one bin of the level it was drawn in (<= (far-near)/n_samples)
+        assert frac4 > 0.90 and frac3 > 0.995 and d[:, :n_in].max() < 2e-2, (frac4, frac3, d[:, :n_in].max())
         assert (np.diff(z[:, :n_in], axis=1) >= 0).all(), 'inner samples must be sorted'
         assert (z[:, 0] >= gold[:, 0] - 1e-5).all() and (z[:, n_in - 1] <= gold[:, n_in - 1] + 1e-5).all()
 
@@ -124,3 +125,42 @@ def test_sdf_values_match_reference_1e4():
     w['SC'][:4096, 217:256] = pe * 0.7071067811865476
     e.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, 4096)
     allclose(w['SSDF'][:4096, 0], want[:, 0].numpy(), 1e-4, 2e-5, 'sdf')
+
+
+@pytest.mark.parametrize('name', list(VAL_FIXTURES))
+def test_validation_render_matches_reference(name):
+    """render_core(is_train=False): depth / normal / shading intermediates / occ_prob_gt (network/renderer.py:465-482)."""
+    from nero_b200.renderer import NeROShapeRenderer
+    g = load_golden(name)
+    cfg = VAL_FIXTURES[name]
+    sd = build_params(cfg, int(g['seed']), int(g['pseed']))
+    net = NeROShapeRenderer(cfg, training=False)
+    net.load_state_dict(sd)
+    net = net.cuda()
+    r = {k: v.to(DEV) for k, v in O.synthetic_rays(int(g['R']), seed=int(g['seed'])).items()}
+    c = O.merged_cfg(cfg)
+    step = int(g['step'])
+    with torch.no_grad():
+        out = net.render_core(r['rays_o'], r['rays_d'], t(g['z_vals']).to(DEV), r['human_poses'], O.get_anneal_val(c, step), step,
+                              is_train=False)
+    keys = [k[4:] for k in g if k.startswith('val_')]
+    assert set(keys) == set(out.keys()), set(keys) ^ set(out.keys())
+    tol = {'gradient_error': (2e-3, 2e-5), 'loss_occ': (1e-3, 1e-6), 'occ_prob_gt': (2e-3, 2e-4), 'normal': (2e-4, 1e-4)}
+    for k in keys:
+        rt, at = tol.get(k, (2e-4, 3e-5))
+        allclose(out[k], g['val_' + k], rt, at, k)
+
+
+def test_sdf_grid_query_matches_oracle():
+    """network.sdf_network.sdf(x) as extract_mesh.py:27 / field.py:1090-1117 use it (value-only, arbitrary points)."""
+    net, g, cfg, sd = make_net('shape_bell_r32')
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(150001, 3, generator=gen) * 2 - 1          # > one workspace chunk, ragged tail
+    got = net.sdf_network.sdf(x.to(DEV))
+    assert got.shape == (150001, 1)
+    with torch.no_grad():
+        want = O.sdf_forward(sd, x[:20000])[..., :1]
+    allclose(got[:20000], want.numpy(), 1e-4, 2e-5, 'sdf grid query')
+    # chunk boundary / tail: same values when queried alone
+    again = net.sdf_network.sdf(x[131000:].to(DEV))
+    assert torch.equal(again, got[131000:])
