@@ -157,6 +157,74 @@ class ShadingParams(nn.Module):
             self.human_light_predictor.set_last_bias(np.log(0.01))
 
 
+class MaterialFeatsParams(nn.Module):
+    """MaterialFeatsNetwork (network/field.py:660-683): module0 = 4x(WN Linear, ReLU) on PE8(x)=51; module1 = 4 WN linears on
+    cat(256, 51), ReLU between, none after the last.  Parameters at Sequential indices 0, 2, 4, 6."""
+
+    def __init__(self, run_dim=256, input_dim=51):
+        super().__init__()
+        self.module0, self.module1 = nn.Module(), nn.Module()
+        for i, a in zip((0, 2, 4, 6), (input_dim, run_dim, run_dim, run_dim)):
+            self.module0.add_module(str(i), WNLinear(nn.Linear(a, run_dim)))
+        for i, a in zip((0, 2, 4, 6), (input_dim + run_dim, run_dim, run_dim, run_dim)):
+            self.module1.add_module(str(i), WNLinear(nn.Linear(a, run_dim)))
+
+    def layers(self):
+        return [getattr(self.module0, str(i)) for i in (0, 2, 4, 6)] + [getattr(self.module1, str(i)) for i in (0, 2, 4, 6)]
+
+
+def _sample_sphere(n):
+    """utils/base_utils.py:800-813 with begin_elevation=0 (upper-hemisphere golden-ratio spiral)."""
+    total = int(n // 0.5)
+    idx = np.arange(total - n, total)
+    return 2 * np.pi * idx * ((np.sqrt(5) - 1.0) / 2.) % (2 * np.pi), np.arcsin(2. * idx / total - 1.)
+
+
+class MCShadingParams(nn.Module):
+    """MCShadingNetwork parameters, `light_pts` buffer and the fixed (az, el) sample tables (network/field.py:694-751)."""
+    default_cfg = {
+        'diffuse_sample_num': 512, 'specular_sample_num': 256, 'human_lights': True, 'light_exp_max': 5.0,
+        'inner_light_exp_max': 5.0, 'outer_light_version': 'direction', 'geometry_type': 'schlick',
+        'reg_change': True, 'change_eps': 0.05, 'change_type': 'gaussian', 'reg_lambda1': 0.005, 'reg_min_max': True,
+        'random_azimuth': True, 'is_real': False,
+    }
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        self.feats_network = MaterialFeatsParams()
+        self.metallic_predictor = PredictorParams(256 + 3, 1)
+        self.roughness_predictor = PredictorParams(256 + 3, 1)
+        self.albedo_predictor = PredictorParams(256 + 3, 3)
+        ver = self.cfg['outer_light_version']
+        if ver not in ('direction', 'sphere_direction'):
+            raise NotImplementedError(ver)
+        self.outer_light = PredictorParams(72 if ver == 'direction' else 144, 3)
+        self.outer_light.set_last_bias(np.log(0.5))
+        if self.cfg['human_lights']:
+            self.human_light = PredictorParams(2 * 2 * 6, 4)
+            self.human_light.set_last_bias(np.log(0.02))
+        self.inner_light = PredictorParams(51 + 72, 3)
+        self.inner_light.set_last_bias(np.log(0.5))
+
+        def table(n):
+            az, el = _sample_sphere(n)
+            return torch.from_numpy(np.stack([az * 0.5 / np.pi, 1 - 2 * el / np.pi], -1).astype(np.float32))
+        # plain attributes in the reference (not in the state_dict), field.py:737-745
+        self.diffuse_direction_samples = table(self.cfg['diffuse_sample_num'])
+        self.specular_direction_samples = table(self.cfg['specular_sample_num'])
+        az, el = _sample_sphere(8192)
+        pts = np.stack([np.cos(az) * np.cos(el), np.sin(az) * np.cos(el), np.sin(el)], -1)
+        self.register_buffer('light_pts', torch.from_numpy(pts.astype(np.float32)))
+
+
+def build_material_state_dict(shader_cfg, seed=6033):
+    """state_dict of a freshly initialised stage-II renderer (keys 'shader_network.*') under torch.manual_seed(seed)."""
+    torch.manual_seed(seed)
+    m = MCShadingParams(shader_cfg)
+    return {'shader_network.' + k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
 class ShapeParams(nn.Module):
     """All stage-I parameters in the reference's module order (network/renderer.py:117-130)."""
 

@@ -22,6 +22,7 @@ warnings.filterwarnings('ignore')
 
 import ref_shim  # noqa: E402
 import nero_oracle as O  # noqa: E402
+import nero_oracle_mat as OM  # noqa: E402
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
@@ -141,6 +142,70 @@ def make_validation_fixture(name, cfg, R, step, seed=6033, pseed=7):
           'occ_gt mean', float(o['occ_prob_gt'].mean()))
 
 
+MATERIAL_FIXTURES = {
+    'material_bell_p24': ({'shader_cfg': {'human_lights': False, 'diffuse_sample_num': 32, 'specular_sample_num': 16}}, 24, [500, 5000]),
+    'material_bear_p16': ({'shader_cfg': {'human_lights': True, 'diffuse_sample_num': 32, 'specular_sample_num': 16}}, 16, [5000]),
+    'material_ggx_p16': ({'shader_cfg': {'human_lights': False, 'diffuse_sample_num': 16, 'specular_sample_num': 16,
+                                         'geometry_type': 'ggx_smith', 'outer_light_version': 'sphere_direction'}}, 16, [5000]),
+}
+
+
+def make_material_fixture(name, cfg, P, steps, seed=6033, pseed=7):
+    """Stage II: the reference's MCShadingNetwork + NeROMaterialRenderer.train_step glue (network/renderer.py:825-848,
+    the renderer object is created without its open3d / dataset constructor) on a synthetic mesh traced by the oracle's
+    brute-force tracer.  The in-function random draws (field.py:782,805,1070,1074) are recorded by re-seeding."""
+    from nero_b200 import params as PR
+    ref_shim.install()
+    from network.renderer import NeROMaterialRenderer
+    scfg = cfg['shader_cfg']
+    verts, tris = OM.test_scene(2)
+    trace_fn = lambda o, d: OM.renderer_trace(verts, tris, o, d)
+    shader = ref_shim.build_reference_mc_shader(dict(scfg), trace_fn, seed=seed)
+    sd_ref = {'shader_network.' + k: v.detach().clone() for k, v in shader.state_dict().items()}
+    mine = PR.build_material_state_dict(scfg, seed=seed)
+    assert list(mine.keys()) == list(sd_ref.keys()) and all(torch.equal(mine[k], sd_ref[k]) for k in sd_ref)
+    sd = O.perturb_params(sd_ref, seed=pseed)
+    shader.load_state_dict({k[len('shader_network.'):]: v for k, v in sd.items()})
+    net = NeROMaterialRenderer.__new__(NeROMaterialRenderer)
+    torch.nn.Module.__init__(net)
+    net.cfg = {**NeROMaterialRenderer.default_cfg, **cfg}
+    net.shader_network = shader
+    batch = OM.synthetic_surface_batch(verts, tris, P, seed=seed)
+    net.train_batch = {'inters': batch['pts'], 'rays_d': batch['rays_d'], 'normals': batch['normals'], 'rgb': batch['rgb'],
+                       'human_poses': batch['human_poses']}
+    net.tbn = 10 ** 9
+    net.cfg['train_ray_num'] = P
+    out = {'param_checksums': param_checksums(sd), 'P': P, 'seed': seed, 'pseed': pseed}
+    out.update({'in_' + k: v for k, v in batch.items()})
+    names = [n for n, _ in net.named_parameters()]
+    c_eps = shader.cfg['change_eps']
+    for step in steps:
+        net.train_batch_i = 0
+        net.zero_grad()
+        torch.manual_seed(seed + step)
+        o = net.train_step(step)
+        loss = sum(torch.mean(v) for k, v in o.items() if k.startswith('loss'))
+        loss.backward()
+        torch.manual_seed(seed + step)
+        pre = f's{step}_'
+        out[pre + 'rand_d'], out[pre + 'rand_s'] = torch.rand(P, 1, 1), torch.rand(P, 1, 1)
+        out[pre + 'rand_ang'] = torch.rand(P, 1)
+        out[pre + 'rand_eps'] = torch.normal(mean=0.0, std=c_eps, size=[P, 1])
+        for k, v in o.items():
+            out[pre + k] = v
+        out[pre + 'loss'] = loss
+        gd = dict(net.named_parameters())
+        out[pre + 'grad_norms'] = np.array([float(gd[n].grad.double().norm()) if gd[n].grad is not None else 0.0 for n in names])
+        for k in ['shader_network.roughness_predictor.6.bias', 'shader_network.feats_network.module0.0.weight_g',
+                  'shader_network.albedo_predictor.6.weight_v', 'shader_network.outer_light.6.bias',
+                  'shader_network.inner_light.0.weight_g', 'shader_network.human_light.6.bias']:
+            if k in gd and gd[k].grad is not None:
+                out[pre + 'grad::' + k] = gd[k].grad.clone()
+    out['param_names'] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **npy(out))
+    print(name, 'saved; loss', {s: float(out[f's{s}_loss']) for s in steps}, 'keys', sorted(o.keys()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     make_encoding_kats()
@@ -150,10 +215,15 @@ def main():
     make_shape_fixture('shape_bell_full_r16', {}, 16, [30000])
     make_validation_fixture('shape_val_bell_r32', {'n_samples': 32, 'n_importance': 32}, 32, 30000)
     make_validation_fixture('shape_val_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}}, 24, 30000)
+    for k, (cfg, P, steps) in MATERIAL_FIXTURES.items():
+        make_material_fixture(k, cfg, P, steps)
 
 
 if __name__ == '__main__':
-    if '--val-only' in sys.argv:
+    if '--material-only' in sys.argv:
+        for k, (cfg, P, steps) in MATERIAL_FIXTURES.items():
+            make_material_fixture(k, cfg, P, steps)
+    elif '--val-only' in sys.argv:
         ref_shim.install()
         make_validation_fixture('shape_val_bell_r32', {'n_samples': 32, 'n_importance': 32}, 32, 30000)
         make_validation_fixture('shape_val_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}}, 24, 30000)

@@ -115,3 +115,14 @@ def build_reference_shape_renderer(cfg=None, seed=6033):
         torch.manual_seed(seed)
         net = NeROShapeRenderer(cfg or {}, training=False)
     return net
+
+
+def build_reference_mc_shader(shader_cfg, trace_fn, seed=6033):
+    """The reference's MCShadingNetwork(cfg, ray_trace_fun) (network/field.py:713-751) under `seed`; `trace_fn` stands in
+    for NeROMaterialRenderer.trace (the third-party ray tracer is not in the container)."""
+    install()
+    with _cwd(REFERENCE_ROOT):
+        from network.field import MCShadingNetwork
+        torch.manual_seed(seed)
+        net = MCShadingNetwork(shader_cfg, trace_fn)
+    return net

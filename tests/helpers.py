@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 import nero_oracle as O
+import nero_oracle_mat as OM
 from nero_b200 import params as P
 
 warnings.filterwarnings('ignore')
@@ -41,3 +42,21 @@ FIXTURE_CFGS = {
 }
 FIXTURE_STEPS = {'shape_bell_r32': [500, 10000, 30000], 'shape_bear_r24': [500, 30000], 'shape_bell_full_r16': [30000]}
 VAL_FIXTURES = {'shape_val_bell_r32': FIXTURE_CFGS['shape_bell_r32'], 'shape_val_bear_r24': FIXTURE_CFGS['shape_bear_r24']}
+MATERIAL_FIXTURES = {
+    'material_bell_p24': ({'shader_cfg': {'human_lights': False, 'diffuse_sample_num': 32, 'specular_sample_num': 16}}, [500, 5000]),
+    'material_bear_p16': ({'shader_cfg': {'human_lights': True, 'diffuse_sample_num': 32, 'specular_sample_num': 16}}, [5000]),
+    'material_ggx_p16': ({'shader_cfg': {'human_lights': False, 'diffuse_sample_num': 16, 'specular_sample_num': 16,
+                                         'geometry_type': 'ggx_smith', 'outer_light_version': 'sphere_direction'}}, [5000]),
+}
+
+
+def build_material_params(shader_cfg, seed=6033, pseed=7):
+    return O.perturb_params(P.build_material_state_dict(shader_cfg, seed=seed), seed=pseed)
+
+
+def material_batch_from_golden(g, dtype=torch.float32):
+    return {k[3:]: t(v, dtype) for k, v in g.items() if k.startswith('in_')}
+
+
+def material_rands(g, step, dtype=torch.float32):
+    return {k: t(g[f's{step}_{k}'], dtype) for k in ('rand_d', 'rand_s', 'rand_ang', 'rand_eps')}

@@ -5,7 +5,9 @@ import pytest
 import torch
 
 import nero_oracle as O
+import nero_oracle_mat as OM
 from helpers import load_golden, build_params, param_checksums, t, rays_from_golden, FIXTURE_CFGS, FIXTURE_STEPS, VAL_FIXTURES
+from helpers import MATERIAL_FIXTURES, build_material_params, material_batch_from_golden, material_rands
 
 
 def test_encoding_kats():
@@ -87,3 +89,34 @@ def test_validation_fixture(name):
     assert set(keys) == set(out.keys())
     for k in keys:
         np.testing.assert_allclose(out[k].numpy().reshape(-1), g['val_' + k].reshape(-1), rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize('name', list(MATERIAL_FIXTURES))
+def test_material_fixture(name):
+    """Stage II oracle (MCShadingNetwork + train-step glue) vs the unmodified reference, same tracer, same random draws."""
+    g = load_golden(name)
+    cfg, steps = MATERIAL_FIXTURES[name]
+    scfg = cfg['shader_cfg']
+    sd = build_material_params(scfg, int(g['seed']), int(g['pseed']))
+    np.testing.assert_allclose(param_checksums(sd), g['param_checksums'], rtol=1e-12)
+    verts, tris = OM.test_scene(2)
+    trace_fn = lambda o, d: OM.renderer_trace(verts, tris, o, d)
+    batch = material_batch_from_golden(g)
+    again = OM.synthetic_surface_batch(verts, tris, int(g['P']), seed=int(g['seed']))
+    assert all(torch.equal(batch[k], again[k]) for k in batch)
+    tabs = (OM.direction_samples(scfg['diffuse_sample_num']), OM.direction_samples(scfg['specular_sample_num']))
+    names = [str(n) for n in g['param_names']]
+    for step in steps:
+        p = {k: v.clone().requires_grad_(k in names) for k, v in sd.items()}
+        out = OM.material_train_outputs(p, cfg, tabs, trace_fn, batch, step, material_rands(g, step))
+        loss = OM.material_training_loss(out)
+        loss.backward()
+        pre = f's{step}_'
+        for k in out:
+            np.testing.assert_allclose(out[k].detach().numpy().reshape(-1), g[pre + k].reshape(-1), rtol=2e-5, atol=2e-6, err_msg=k)
+        np.testing.assert_allclose(float(loss), float(g[pre + 'loss']), rtol=1e-6)
+        gn = np.array([float(p[n].grad.double().norm()) if p[n].grad is not None else 0.0 for n in names])
+        np.testing.assert_allclose(gn, g[pre + 'grad_norms'], rtol=2e-4, atol=1e-9)
+        for k in g:
+            if k.startswith(pre + 'grad::'):
+                np.testing.assert_allclose(p[k.split('::')[1]].grad.numpy(), g[k], rtol=2e-4, atol=1e-7)
