@@ -169,6 +169,53 @@ int nero_occ_select(const float* pts, const float* Y8, int ldy, int sdf_col, con
 int nero_occ_loss(const float* occ_prob, const float* gt, const int* sel, const int* p_ptr, int p_cap, float* loss_sum, float* docc_sign,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stage II (material estimation).  Replaces MCShadingNetwork.shade_mixed / get_lights (network/field.py:858-1003) around
+ * the light MLPs and the third-party ray tracer called at network/renderer.py:676,720.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Host-side BVH build (init time).  verts [V,3] fp32 and tris [T,3] int32 in HOST memory; outputs in caller-allocated
+ * HOST memory: nodes_out 2*T records of 32 bytes, tri_out T*12 floats (v0,e1,e2 as float4), tri_id_out T ints. */
+int nero_bvh_build_host(const float* verts, int V, const int* tris, int T, void* nodes_out, float* tri_out, int* tri_id_out, int* n_nodes);
+/* Closest hit of n_rays rays (device pointers).  pos_depth [n,4] = (hit position, depth; depth = miss_depth on a miss),
+ * nrm_hit [n,4] = (unit face normal, hit flag); flip != 0 negates the normal (renderer.py:722-723). */
+int nero_bvh_trace(const void* nodes, const float* tris, int n_rays, const float* org, int ldo, const float* dir, int ldd,
+                   float* pos_depth, float* nrm_hit, float miss_depth, int flip, void* stream);
+
+typedef struct nero_mc_params {
+  const float* pts; const float* normals; const float* view; const float* rough;   /* per point [P,3] x3, [P]            */
+  const float* poses;                                                               /* [P,12] capturer poses or NULL     */
+  const float* rand_d; const float* rand_s;                                         /* [P] azimuth draws or NULL         */
+  const float* tab_d; const float* tab_s;                                           /* [Sd,2], [Ss,2] (az, el) in [0,1]  */
+  int P, Sd, Ss;
+  int ggx_smith, sphere_dir, human;
+  float* org; float* dir;                                                           /* per ray [N,4], N = P*(Sd+Ss)      */
+  const float* pos_depth; const float* nrm_hit;                                     /* nero_bvh_trace outputs            */
+  int* slot;                                                                        /* >= 0 outer row, < 0 ~inner row    */
+  int* blk_cnt; int* blk_off; int* counts;                                          /* [ceil(N/256)] x2, [2]=(hit,miss)  */
+  float* EO; int ldeo; float* EH; int ldeh; float* hhit; float* EI; int ldei;       /* MLP input rows                    */
+  const float* OUT_O; const float* OUT_H; const float* OUT_I;                       /* MLP outputs [.,4]                 */
+  float exp_max_o, exp_max_i;
+  float* LD; float* LS; float* LSF;                                                 /* estimator means [P,3]             */
+  const float* dLD; const float* dLS; const float* dLSF;
+  float* DPRE_O; float* DPRE_H; float* DPRE_I;                                      /* pre-activation output grads [.,4] */
+  float* dA;                                                                        /* [P] d/d roughness (weights part)  */
+  const float* dEO; const float* dEH; const float* dEI;                             /* MLP input grads                   */
+  float* dA2;                                                                       /* [P] d/d roughness via directions  */
+} nero_mc_params;
+/* sample_diffuse_directions / sample_specular_directions (field.py:768-812): dir, org = pts + 1e-5*dir */
+int nero_mc_sample(const nero_mc_params* q, void* stream);
+/* hit/miss counts per 256-ray block + exclusive scan + totals (deterministic compaction, field.py:866-879 masks) */
+int nero_mc_classify(const nero_mc_params* q, void* stream);
+/* row assignment + encodings: outer IDE(dir,0) [+IDE(sphere point)] (+ human IPE), inner PE8(hit) | IDE(reflection) */
+int nero_mc_fill(const nero_mc_params* q, void* stream);
+/* LD / LS / LSF means over the samples (field.py:941-984) */
+int nero_mc_combine_fwd(const nero_mc_params* q, void* stream);
+int nero_mc_combine_bwd(const nero_mc_params* q, void* stream);
+/* gradient reaching the roughness through the specular directions (IDE / IPE / reflection backward) */
+int nero_mc_dir_bwd(const nero_mc_params* q, void* stream);
+/* MaterialFeatsNetwork inputs (field.py:660-689): PE8 rows, skip-concat tail, xyz for the predictor input */
+int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,23 @@ int reg_fill(const float* rays_o, const float* rays_d, const float* z_vals, int 
              float* X0, int ldx, float* H4, int ldh, cudaStream_t st);
 int points_fill(const float* pts3, int N, float* pts, int* ray_in, float* X0, int ldx, float* Y8, int ldy, float* H4, int ldh, cudaStream_t st);
 struct ChainParams;
+int set_ide_table_mc(const float* mat17x36_host);
+int bvh_build_host(const float* verts, int V, const int* tris, int T, void* nodes_out, float* tri_out, int* tri_id_out, int* n_nodes);
+struct BvhNode;
+struct TraceParams {
+  const BvhNode* nodes; const float4* tris; int n_rays;
+  const float* org; int ldo; const float* dir; int ldd;
+  float4* pos_depth; float4* nrm_hit;
+  float miss_depth; int flip;
+};
+int bvh_trace(const TraceParams& q, cudaStream_t st);
+int mc_sample(const ::nero_mc_params& q, cudaStream_t st);
+int mc_classify(const ::nero_mc_params& q, cudaStream_t st);
+int mc_fill(const ::nero_mc_params& q, cudaStream_t st);
+int mc_combine_fwd(const ::nero_mc_params& q, cudaStream_t st);
+int mc_combine_bwd(const ::nero_mc_params& q, cudaStream_t st);
+int mc_dir_bwd(const ::nero_mc_params& q, cudaStream_t st);
+int mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, cudaStream_t st);
 int chain_dispatch(const ChainParams& p, cudaStream_t stream);
 int occ_loss(const float* occ_prob, const float* gt, const int* sel, const int* p_ptr, int p_cap, float* loss_sum, float* docc_sign,
              cudaStream_t st);
@@ -174,7 +191,30 @@ int nero_colsum(const float* X, int ldx, int ncol, const float* w, int ldw, cons
   return colsum(X, ldx, ncol, w, ldw, m_ptr, m_cap, out, (cudaStream_t)stream);
 }
 
-int nero_set_ide_table(const float* mat17x36_host) { return set_ide_table(mat17x36_host); }
+int nero_set_ide_table(const float* mat17x36_host) {
+  const int rc = set_ide_table(mat17x36_host);
+  return rc != NERO_OK ? rc : set_ide_table_mc(mat17x36_host);
+}
+int nero_bvh_build_host(const float* verts, int V, const int* tris, int T, void* nodes_out, float* tri_out, int* tri_id_out, int* n_nodes) {
+  if (!verts || !tris || !nodes_out || !tri_out || !tri_id_out || !n_nodes) return NERO_ERR_ARG;
+  return bvh_build_host(verts, V, tris, T, nodes_out, tri_out, tri_id_out, n_nodes);
+}
+int nero_bvh_trace(const void* nodes, const float* tris, int n_rays, const float* org, int ldo, const float* dir, int ldd,
+                   float* pos_depth, float* nrm_hit, float miss_depth, int flip, void* stream) {
+  if (!nodes || !tris || (n_rays > 0 && (!org || !dir || !pos_depth || !nrm_hit))) return NERO_ERR_ARG;
+  TraceParams q{reinterpret_cast<const BvhNode*>(nodes), reinterpret_cast<const float4*>(tris), n_rays, org, ldo, dir, ldd,
+                reinterpret_cast<float4*>(pos_depth), reinterpret_cast<float4*>(nrm_hit), miss_depth, flip};
+  return bvh_trace(q, (cudaStream_t)stream);
+}
+int nero_mc_sample(const nero_mc_params* q, void* stream) { return q ? mc_sample(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_mc_classify(const nero_mc_params* q, void* stream) { return q ? mc_classify(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_mc_fill(const nero_mc_params* q, void* stream) { return q ? mc_fill(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_mc_combine_fwd(const nero_mc_params* q, void* stream) { return q ? mc_combine_fwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_mc_combine_bwd(const nero_mc_params* q, void* stream) { return q ? mc_combine_bwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_mc_dir_bwd(const nero_mc_params* q, void* stream) { return q ? mc_dir_bwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, void* stream) {
+  return mat_prep(pts, M, X, ldx, CAT, ldc, Y, ldy, (cudaStream_t)stream);
+}
 
 int nero_chain(const void* chain_params_host, void* stream) {
   if (!chain_params_host) return NERO_ERR_ARG;

@@ -437,3 +437,55 @@ def _chain_unfused(A0, k_valid0, layers, m_ptr, m_cap):
             if d['csrc'] is not None:
                 nxt[:M, nm:256] = d['csrc'].t[:M, d['csrc'].c0 + nm:d['csrc'].c0 + 256]
             cur = Mat(nxt)
+
+
+# ------------------------------------------------------------------------------------------------ stage II (k_mcshade.cu, k_bvh.cu)
+_vp, _ci, _cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+
+class McParams(ctypes.Structure):
+    """Mirror of nero_mc_params (include/nero_b200.h)."""
+    _fields_ = [('pts', _vp), ('normals', _vp), ('view', _vp), ('rough', _vp), ('poses', _vp), ('rand_d', _vp), ('rand_s', _vp),
+                ('tab_d', _vp), ('tab_s', _vp), ('P', _ci), ('Sd', _ci), ('Ss', _ci), ('ggx_smith', _ci), ('sphere_dir', _ci),
+                ('human', _ci), ('org', _vp), ('dir', _vp), ('pos_depth', _vp), ('nrm_hit', _vp), ('slot', _vp), ('blk_cnt', _vp),
+                ('blk_off', _vp), ('counts', _vp), ('EO', _vp), ('ldeo', _ci), ('EH', _vp), ('ldeh', _ci), ('hhit', _vp), ('EI', _vp),
+                ('ldei', _ci), ('OUT_O', _vp), ('OUT_H', _vp), ('OUT_I', _vp), ('exp_max_o', _cf), ('exp_max_i', _cf), ('LD', _vp),
+                ('LS', _vp), ('LSF', _vp), ('dLD', _vp), ('dLS', _vp), ('dLSF', _vp), ('DPRE_O', _vp), ('DPRE_H', _vp), ('DPRE_I', _vp),
+                ('dA', _vp), ('dEO', _vp), ('dEH', _vp), ('dEI', _vp), ('dA2', _vp)]
+
+    def set(self, **kw):
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                v = v.data_ptr()
+            elif isinstance(v, Mat):
+                v = v.t.data_ptr() + 4 * v.c0
+            setattr(self, k, v)
+        return self
+
+
+def mc(name, params: McParams):
+    """Launch one of the nero_mc_* kernels on the current stream."""
+    global launch_count
+    if DRY_RUN:
+        getattr(lib, name)
+        return
+    rc = getattr(lib, name)(ctypes.byref(params), _stream())
+    _check(rc, name)
+    launch_count += 1
+
+
+def bvh_build(verts, tris):
+    """Host BVH build through the C ABI: numpy verts [V,3] f32, tris [T,3] i32 -> (nodes uint8 [n,32], tri float32 [T,12],
+    tri_ids int32 [T]) as numpy arrays ready to upload."""
+    import numpy as np
+    verts = np.ascontiguousarray(verts, np.float32)
+    tris = np.ascontiguousarray(tris, np.int32)
+    T = tris.shape[0]
+    nodes = np.zeros((2 * T, 32), np.uint8)
+    tri = np.zeros((T, 12), np.float32)
+    ids = np.zeros(T, np.int32)
+    n = ctypes.c_int(0)
+    rc = lib.nero_bvh_build_host(verts.ctypes.data_as(_vp), verts.shape[0], tris.ctypes.data_as(_vp), T, nodes.ctypes.data_as(_vp),
+                                 tri.ctypes.data_as(_vp), ids.ctypes.data_as(_vp), ctypes.byref(n))
+    _check(rc, 'nero_bvh_build_host')
+    return nodes[:n.value].copy(), tri, ids

@@ -1,0 +1,111 @@
+"""GPU parity of stage II (material estimation): BVH tracing against the oracle's exhaustive tracer, and the Monte-Carlo
+shading train step (NeROMaterialRenderer.shade_batch -> C ABI kernels) against the golden vectors of the unmodified
+reference `MCShadingNetwork` (same mesh, same tracer semantics, same random draws).
+
+Tolerances: colours / lights 2e-4 relative + 3e-5 absolute (split-bf16 MLPs, ~1e-5 GEMM error, means over 48 samples);
+parameter gradients 3e-3 norm-wise (ReLU-boundary flips of single rows move small tensors by ~1e-3).
+"""
+import numpy as np
+import pytest
+import torch
+
+import nero_oracle as O
+import nero_oracle_mat as OM
+from helpers import load_golden, t, MATERIAL_FIXTURES, build_material_params, material_batch_from_golden, material_rands
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def allclose(got, want, rtol, atol, name):
+    got = got.detach().float().cpu().numpy().reshape(-1)
+    want = np.asarray(want, dtype=np.float32).reshape(-1)
+    assert got.shape == want.shape, f'{name}: shape {got.shape} vs {want.shape}'
+    viol = np.abs(got - want) - (atol + rtol * np.abs(want))
+    assert viol.max() <= 0, f'{name}: max violation {viol.max():.3e}, max abs err {np.abs(got - want).max():.3e}'
+
+
+def make_net(name):
+    from nero_b200.material import NeROMaterialRenderer
+    g = load_golden(name)
+    cfg, steps = MATERIAL_FIXTURES[name]
+    verts, tris = OM.test_scene(2)
+    net = NeROMaterialRenderer(cfg, is_train=False, mesh=(verts, tris))
+    net.load_state_dict(build_material_params(cfg['shader_cfg'], int(g['seed']), int(g['pseed'])))
+    return net.cuda(), g, cfg, steps, (verts, tris)
+
+
+@pytest.mark.parametrize('subdiv', [2, 4])
+def test_bvh_trace_matches_bruteforce(subdiv):
+    from nero_b200.material import NeROMaterialRenderer
+    verts, tris = OM.test_scene(subdiv)
+    net = NeROMaterialRenderer({'shader_cfg': {'diffuse_sample_num': 8, 'specular_sample_num': 8}}, is_train=False, mesh=(verts, tris)).cuda()
+    n = 20000 if subdiv == 2 else 6000
+    rays = O.synthetic_rays(n, seed=11)
+    o, d = rays['rays_o'], rays['rays_d']
+    # a second batch starting ON the surface (secondary-ray regime: tiny offsets, grazing directions)
+    pi, pn, pd, ph = OM.renderer_trace(verts, tris, o[:2000], d[:2000])
+    g = torch.Generator().manual_seed(3)
+    d2 = torch.nn.functional.normalize(torch.randn(2000, 3, generator=g), dim=-1)
+    o = torch.cat([o, pi + d2 * 1e-5])
+    d = torch.cat([d, d2])
+    want = OM.renderer_trace(verts, tris, o, d)
+    got = [x.cpu() for x in net.trace(o.to(DEV), d.to(DEV))]
+    hit_w, hit_g = want[3][:, 0], got[3][:, 0]
+    agree = hit_w == hit_g
+    assert agree.float().mean() > 0.9995, f'hit/miss disagreement on {(~agree).sum()} of {agree.numel()} rays'
+    both = hit_w & hit_g
+    assert both.sum() > 1000 and (~hit_w).sum() > 100
+    dd = (got[2][both] - want[2][both]).abs()
+    same_tri = dd[:, 0] < 1e-4
+    assert same_tri.float().mean() > 0.999           # edge ties may pick the neighbour triangle
+    idx = torch.nonzero(both)[:, 0][same_tri]
+    assert (got[0][idx] - want[0][idx]).abs().max() < 1e-4
+    nd = (got[1][idx] * want[1][idx]).sum(-1)
+    assert (nd > 0.9999).float().mean() > 0.998
+    miss = ~hit_w & ~hit_g
+    assert (got[2][miss] == 10.0).all() and (got[1][miss] == 0).all()
+
+
+@pytest.mark.parametrize('name', list(MATERIAL_FIXTURES))
+def test_material_train_step_matches_reference(name):
+    net, g, cfg, steps, _ = make_net(name)
+    batch = {k: v.to(DEV) for k, v in material_batch_from_golden(g).items()}
+    names = [str(n) for n in g['param_names']]
+    for step in steps:
+        net.zero_grad()
+        rands = {k: v.to(DEV) for k, v in material_rands(g, step).items()}
+        out = net.shade_batch(batch, step, rands)
+        pre = f's{step}_'
+        for k in ('metallic', 'roughness', 'albedo'):
+            allclose(out[k], g[pre + k], 1e-4, 1e-5, k)
+        for k in ('rgb_pr', 'diffuse_light', 'specular_light', 'diffuse_color', 'specular_color', 'approximate_light', 'loss_rgb',
+                  'loss_diffuse_light'):
+            allclose(out[k], g[pre + k], 2e-4, 3e-5, k)
+        allclose(out['loss_mat_reg'], g[pre + 'loss_mat_reg'], 2e-3, 2e-8, 'loss_mat_reg')
+        allclose(out['human_lights'], g[pre + 'human_lights'], 2e-4, 1e-6, 'human_lights')
+        loss = sum(torch.mean(v) for k, v in out.items() if k.startswith('loss'))
+        assert abs(float(loss.detach()) - float(g[pre + 'loss'])) <= 1e-4 * abs(float(g[pre + 'loss']))
+        loss.backward()
+        torch.cuda.synchronize()
+        P = dict(net.named_parameters())
+        gn = np.array([float(P[n].grad.double().norm()) if P[n].grad is not None else 0.0 for n in names])
+        ref = g[pre + 'grad_norms']
+        bad = np.abs(gn - ref) > 3e-3 * ref + 1e-9
+        assert not bad.any(), [(names[i], gn[i], ref[i]) for i in np.nonzero(bad)[0][:8]]
+        for k in g:
+            if k.startswith(pre + 'grad::'):
+                want = g[k]
+                got = P[k.split('::')[1]].grad.cpu().numpy()
+                assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max() + 1e-10, k
+
+
+def test_material_eval_mode_is_deterministic():
+    """is_train=False: no azimuth jitter, no regulariser (field.py:781, renderer.py:804-807); two calls agree bit for bit."""
+    net, g, cfg, steps, _ = make_net('material_bell_p24')
+    b = {k: v.to(DEV) for k, v in material_batch_from_golden(g).items()}
+    with torch.no_grad():
+        a = net.shade(b['pts'], -b['rays_d'], b['normals'], b['human_poses'], False)
+        c = net.shade(b['pts'], -b['rays_d'], b['normals'], b['human_poses'], False)
+    assert all(torch.equal(a[k], c[k]) for k in a)
+    assert float(a['rgb_pr'].min()) >= 0 and bool(torch.isfinite(a['rgb_pr']).all())
