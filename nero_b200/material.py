@@ -187,7 +187,7 @@ class MaterialEngine:
 
     # ------------------------------------------------------------------ material MLPs
     def _alloc_materials(self, M):
-        if self.mcap == M:
+        if self.mcap is not None and self.mcap >= M:      # workspaces only grow
             return
         z = lambda *s: torch.zeros(*s, device=self.dev)
         names = ['met', 'rough', 'alb']
@@ -209,27 +209,29 @@ class MaterialEngine:
         self.m_met.forward(y, w['ACT']['met'], Mat(w['OUT'], O_MET), None, M)
         self.m_rough.forward(y, w['ACT']['rough'], Mat(w['OUT'], O_ROUGH), None, M)
         self.m_alb.forward(y, w['ACT']['alb'], Mat(w['OUT'], O_ALB), None, M)
-        o = w['OUT']
+        o = w['OUT'][:M]
+        self.m_rows = M
         return o[:, O_MET:O_MET + 1].clone(), o[:, O_ROUGH:O_ROUGH + 1].clone(), o[:, O_ALB:O_ALB + 3].clone()
 
     def materials_backward(self, d_met, d_rough, d_alb):
-        w, M = self.mw, self.mcap
+        w, M = self.mw, self.m_rows
         self.grads.ensure()
-        o, d = w['OUT'], w['DOUT']
+        o, d = w['OUT'][:M], w['DOUT'][:M]
         sg = lambda y, g: g * y * (1.0 - y)          # sigmoid'(x) from the post-activation value
         d[:, O_MET:O_MET + 1] = sg(o[:, O_MET:O_MET + 1], d_met)
         d[:, O_ROUGH:O_ROUGH + 1] = sg(o[:, O_ROUGH:O_ROUGH + 1], d_rough)
         d[:, O_ALB:O_ALB + 3] = sg(o[:, O_ALB:O_ALB + 3], d_alb)
         y, dy = Mat(w['FY']), Mat(w['dFY'])
         a = (w['dHa'], w['dHb'])
-        self.m_rough.backward(self.ws, Mat(d, O_ROUGH), y, w['ACT']['rough'], *a, None, M, dX=dy, dx_ncol=256, dHc=w['dHc'])
-        self.m_met.backward(self.ws, Mat(d, O_MET), y, w['ACT']['met'], *a, None, M, dX=dy, dx_ncol=256, dx_addend=dy, dHc=w['dHc'])
-        self.m_alb.backward(self.ws, Mat(d, O_ALB), y, w['ACT']['alb'], *a, None, M, dX=dy, dx_ncol=256, dx_addend=dy, dHc=w['dHc'])
+        dm = w['DOUT']
+        self.m_rough.backward(self.ws, Mat(dm, O_ROUGH), y, w['ACT']['rough'], *a, None, M, dX=dy, dx_ncol=256, dHc=w['dHc'])
+        self.m_met.backward(self.ws, Mat(dm, O_MET), y, w['ACT']['met'], *a, None, M, dX=dy, dx_ncol=256, dx_addend=dy, dHc=w['dHc'])
+        self.m_alb.backward(self.ws, Mat(dm, O_ALB), y, w['ACT']['alb'], *a, None, M, dX=dy, dx_ncol=256, dx_addend=dy, dHc=w['dHc'])
         self.feats.backward(self.ws, w, M)
 
     # ------------------------------------------------------------------ Monte-Carlo lights
     def _alloc_lights(self, P):
-        if self.cap == P:
+        if self.cap is not None and self.cap >= P:        # workspaces only grow
             return
         S = self.Sd + self.Ss
         N = P * S
@@ -291,7 +293,7 @@ class MaterialEngine:
             self.m_inner.forward(Mat(w['EI']), [a[n_miss:] for a in A], Mat(w['OUT_I']), None, n_hit)
         ops.mc('nero_mc_combine_fwd', q)
         self.state = st
-        return w['LD'].clone(), w['LS'].clone(), w['LSF'].clone()
+        return w['LD'][:P].clone(), w['LS'][:P].clone(), w['LSF'][:P].clone()
 
     def human_lights_output(self):
         """outputs['human_lights'] of shade_mixed (field.py:988): hl*hw of every escaping ray, or zeros [1,3]."""
@@ -323,7 +325,7 @@ class MaterialEngine:
             self.m_inner.backward(self.ws, Mat(w['DPRE_I']), Mat(w['EI']), [a[n_miss:] for a in A], D[0][n_miss:], D[1][n_miss:], None, n_hit,
                                   dX=Mat(w['dEI'], 52), dx_ncol=72, dHc=D[2][n_miss:])
         ops.mc('nero_mc_dir_bwd', q)
-        return w['dA'] + w['dA2']
+        return w['dA'][:st['P']] + w['dA2'][:st['P']]
 
 
 class _MaterialsFn(torch.autograd.Function):
@@ -416,13 +418,25 @@ class NeROMaterialRenderer(nn.Module):
         white = torch.sum(torch.abs(diffuse_lights - torch.mean(diffuse_lights, dim=-1, keepdim=True)), dim=-1)
         return white * self.cfg['reg_diffuse_light_lambda']
 
-    def predict_materials(self, pts):
+    def query_materials(self, pts):
         """MCShadingNetwork.predict_materials (field.py:896-903) on arbitrary points (no gradient bookkeeping)."""
         e = self.engine
         e.prepare_weights()
         with torch.no_grad():
             m, r, a = e.materials_forward(pts.reshape(-1, 3).float().contiguous())
         return m, r * (1.0 - 0.04 ** 2) + 0.04 ** 2, a
+
+    def predict_materials(self, batch_size=8192):
+        """Per-vertex materials of the mesh for the export scripts (renderer.py:903-915): sqrt of the predicted (squared)
+        roughness, numpy arrays."""
+        verts = torch.from_numpy(self._mesh[0]).to(self.shader_network.light_pts.device)
+        outs = {'metallic': [], 'roughness': [], 'albedo': []}
+        for vi in range(0, verts.shape[0], batch_size):
+            m, r, a = self.query_materials(verts[vi:vi + batch_size])
+            outs['metallic'].append(m.cpu().numpy())
+            outs['roughness'].append(torch.sqrt(torch.clamp(r, min=1e-7)).cpu().numpy())
+            outs['albedo'].append(a.cpu().numpy())
+        return {k: np.concatenate(v, 0) for k, v in outs.items()}
 
     def shade(self, pts, view_dirs, normals, human_poses, is_train, step=None, rands=None):
         """MCShadingNetwork.forward + material_regularization inputs (field.py:1005-1009, renderer.py:804-807).
@@ -555,9 +569,40 @@ class NeROMaterialRenderer(nn.Module):
             self._shuffle_train_batch()
         return out
 
+    def render_rays(self, ray_batch, h, w):
+        """The chunk loop of test_step (renderer.py:854-885) over an is_train=False ray batch (with 'hit_mask')."""
+        dev = self.shader_network.light_pts.device
+        rb = {k: v.to(dev) for k, v in ray_batch.items()}
+        trn = self.cfg['test_ray_num']
+        keys = {'rgb_gt': 3, 'rgb_pr': 3, 'specular_light': 3, 'specular_color': 3, 'diffuse_light': 3, 'diffuse_color': 3, 'albedo': 3,
+                'metallic': 1, 'roughness': 1}
+        outs = {k: [] for k in keys}
+        rn = rb['rays_o'].shape[0]
+        with torch.no_grad():
+            for ri in range(0, rn, trn):
+                hit = rb['hit_mask'][ri:ri + trn]
+                cur = {k: torch.zeros(hit.shape[0], d, device=dev) for k, d in keys.items()}
+                if torch.sum(hit) > 0:
+                    sl = lambda k: rb[k][ri:ri + trn][hit]
+                    so = self.shade(sl('inters'), -sl('rays_d'), sl('normals'), sl('human_poses'), False)
+                    cur['rgb_gt'][hit] = sl('rgb')
+                    for k in ('rgb_pr', 'specular_light', 'specular_color', 'diffuse_color', 'diffuse_light', 'albedo', 'metallic'):
+                        cur[k][hit] = so[k]
+                    cur['roughness'][hit] = torch.sqrt(so['roughness'])      # predictions are squared roughness
+                for k in keys:
+                    outs[k].append(cur[k])
+        return {k: torch.cat(v, 0).reshape(h, w, -1) for k, v in outs.items()}
+
+    def test_step(self, index):
+        """renderer.py:850-887 (needs the host repo's database for the test image)."""
+        from network.renderer import imgs_info_slice
+        info = imgs_info_slice(self.test_imgs_info, torch.from_numpy(np.asarray([index], np.int64)))
+        _, _, h, w = info['imgs'].shape
+        return self.render_rays(self._construct_ray_batch(info, 'cpu', False), h, w)
+
     def forward(self, data):
-        if 'eval' in data:
-            raise NotImplementedError('stage-II validation render (renderer.py:850-887) is not part of the B200 path yet')
+        if 'eval' in data:        # renderer.py:889-901
+            return self.test_step(data['index'])
         return self.train_step(data['step'])
 
 

@@ -290,4 +290,9 @@ class NeROShapeRenderer(nn.Module):
         return self.train_step(data['step'])
 
 
-name2renderer = {'shape': NeROShapeRenderer}
+def _material_renderer(*a, **k):
+    from .material import NeROMaterialRenderer
+    return NeROMaterialRenderer(*a, **k)
+
+
+name2renderer = {'shape': NeROShapeRenderer, 'material': _material_renderer}   # network/renderer.py:917-920
