@@ -10,6 +10,8 @@
 // The optional second pair implements the double-backward term of the SDF network,
 //   dW_k = abar_k^T h_k + v_k^T ubar_k      (SURVEY.md Appendix A.3, K4),
 // in ONE accumulator.  Column sums of dY (bias gradient) are produced by the dY producer threads for free.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -221,6 +223,203 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
   if (warp == kWgProdWarps) tmem_dealloc<256>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// MN-major variant.  Both operands are contracted over their ROW index (samples), i.e. in memory the MMA's M / N
+// dimension (features) is the contiguous one: that is exactly an MN-major UMMA operand.  Producers therefore copy rows
+// as they lie -- two 16-byte global loads (8 features of one sample), split to bf16 hi/lo, one 16-byte shared store per
+// plane into the MN-major SWIZZLE_128B atom -- instead of transposing with scalar loads.
+// Stage layout per plane: [feature block of 64][sample group of 8][8 rows x 128 B]  (SBO = 1024, LBO = 8192).
+// Requires 16-byte aligned rows (ld % 4 == 0, column origin % 4 == 0); wgrad_dispatch checks and otherwise uses the
+// transposing kernel above.
+constexpr uint32_t kMnSbo = 1024, kMnLbo = (WG_BK / 8) * 1024;
+
+__device__ __forceinline__ uint32_t mn_chunk_offset(uint32_t chunk, uint32_t s) {   // chunk = feature/8, s = sample in stage
+  const uint32_t r = s & 7u;
+  return (chunk >> 3) * kMnLbo + (s >> 3) * kMnSbo + r * 128u + (((chunk & 7u) ^ r) << 4);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const WgradParams p) {
+  using Cfg = WgCfg<NW>;
+  constexpr int STAGES = Cfg::stages;
+  constexpr int CB = NW / 8;                 // 16-byte chunks per X row
+  constexpr int SPW = 32 / CB;               // X sample rows per warp instruction
+  constexpr int TASKS = 32 + WG_BK / SPW;    // per stage: 32 dY tasks (2 sample rows each) + X tasks
+  constexpr int TPW = TASKS / kWgProdWarps;  // tasks per warp: 6 / 4 / 3
+  static_assert(TASKS % kWgProdWarps == 0 && TPW >= 2, "task split");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::stage_bytes + 256);   // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int M = p.m_ptr ? *p.m_ptr : p.m_cap;
+  if (M > p.m_cap) M = p.m_cap;
+  const int P = gridDim.x;
+  const int n0 = p.n0 + int(blockIdx.y) * WG_BM;
+  const int total_chunks = (M + WG_BK - 1) / WG_BK;
+  const int cpp = (total_chunks + P - 1) / P;
+  const int c_begin = min(total_chunks, int(blockIdx.x) * cpp), c_end = min(total_chunks, c_begin + cpp);
+  const int npairs = p.dY2 ? 2 : 1;
+  const int nc1 = c_end - c_begin;
+  const int nchunks = nc1 * npairs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kWgProdWarps); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 128) s_bias[threadIdx.x] = 0.0f;
+  if (warp == kWgProdWarps) tmem_alloc<256>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWgProdWarps) {
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // this lane's role in each of its tasks (constant over stages)
+    const uint32_t a_chunk = lane & 15, a_sub = lane >> 4;
+    const uint32_t b_chunk = lane % CB, b_sub = lane / CB;
+    const int a_col = n0 + int(a_chunk) * 8, b_col = p.k0 + int(b_chunk) * 8;
+    for (int g = 0; g < nchunks; ++g) {
+      const int s = g % STAGES;
+      const int pair = g / nc1;
+      const int chunk = c_begin + g % nc1;
+      const int s0 = chunk * WG_BK;
+      uint8_t* st = smem + s * Cfg::stage_bytes;
+      const float* srcA = pair ? p.dY2 : p.dY;
+      const int ldA = pair ? p.ldy2 : p.ldy;
+      const float* srcB = pair ? p.X2 : p.X;
+      const int ldB = pair ? p.ldx2 : p.ldx;
+      float4 v[TPW][2];
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        const int t = warp + kWgProdWarps * i;
+        const bool isA = t < 32;                                 // warp-uniform
+        const int sl = isA ? 2 * t + int(a_sub) : (t - 32) * SPW + int(b_sub);
+        const int srow = s0 + sl;
+        const int col = isA ? a_col : b_col;
+        const int lim = isA ? p.n_valid : p.k_valid;
+        const float* rp = (isA ? srcA : srcB) + size_t(srow) * (isA ? ldA : ldB) + col;
+        const bool rok = srow < M;
+        v[i][0] = (rok && col < lim) ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i][1] = (rok && col + 4 < lim) ? __ldg(reinterpret_cast<const float4*>(rp + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        const int t = warp + kWgProdWarps * i;
+        const bool isA = t < 32;
+        const int sl = isA ? 2 * t + int(a_sub) : (t - 32) * SPW + int(b_sub);
+        const int col = isA ? a_col : b_col;
+        const int lim = isA ? p.n_valid : p.k_valid;
+        float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (col + j >= lim) x[j] = 0.f;      // partial float4 at the valid-column boundary
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wg_split2(x[2 * j], x[2 * j + 1], hw[j], lw[j]);
+        uint8_t* hi = isA ? st : st + 2 * kWgABytes;
+        uint8_t* lo = isA ? st + kWgABytes : st + 2 * kWgABytes + Cfg::b_plane;
+        const uint32_t off = mn_chunk_offset(isA ? a_chunk : b_chunk, uint32_t(sl));
+        *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        if (isA && pair == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bsum[j] += x[j];
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], 16);
+      if (lane < 16) atomicAdd(&s_bias[a_chunk * 8 + j], bsum[j]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
+    if (warp < 4) {
+      // -------- epilogue: TMEM -> partial tile in HBM (identical to the transposing kernel)
+      mbar_wait(tfull, 0);
+      tcgen05_fence_after();
+      const int pw = warp;
+      const int orow = n0 + pw * 32 + lane;
+      float* prow = p.partial + (size_t(blockIdx.x) * p.rows_partial + orow) * p.ld_partial + p.k0;
+      const uint32_t taddr = tmem_base + (uint32_t(pw * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < (NW + 31) / 32; ++cc) {
+        float v[32];
+        if (nchunks > 0) {
+          tmem_ld32(taddr + cc * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+        }
+        if (orow < p.rows_partial) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (cc * 32 + j < NW) *reinterpret_cast<float4*>(prow + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      if (p.bias_partial && p.k0 == 0 && orow < p.rows_partial)
+        p.bias_partial[size_t(blockIdx.x) * p.rows_partial + orow] = s_bias[pw * 32 + lane];
+    }
+  } else {
+    // -------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16_mn(WG_BM, NW);
+    for (int g = 0; g < nchunks; ++g) {
+      const int s = g % STAGES;
+      mbar_wait(&full[s], (g / STAGES) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::stage_bytes);
+        const uint32_t a_lo = a_hi + kWgABytes;
+        const uint32_t b_hi = a_hi + 2 * kWgABytes;
+        const uint32_t b_lo = b_hi + Cfg::b_plane;
+#pragma unroll
+        for (int k = 0; k < WG_BK / 16; ++k) {     // 16 samples = two 8-row groups per MMA
+          const uint32_t ko = k * 2 * kMnSbo;
+          const uint64_t dah = make_desc_mn_sw128(a_hi + ko, kMnLbo, kMnSbo), dal = make_desc_mn_sw128(a_lo + ko, kMnLbo, kMnSbo);
+          const uint64_t dbh = make_desc_mn_sw128(b_hi + ko, kMnLbo, kMnSbo), dbl = make_desc_mn_sw128(b_lo + ko, kMnLbo, kMnSbo);
+          umma_bf16(tmem_base, dal, dbh, idesc, (g | k) != 0);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1);
+        }
+        umma_commit(&empty[s]);
+        if (g == nchunks - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+    }
+    if (nchunks == 0 && elect_one()) mbar_arrive(tfull);
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kWgProdWarps) tmem_dealloc<256>(tmem_base);
+}
+
+template <int NW>
+static int launch_wgrad_mn(const WgradParams& p, int P, int n_tiles, cudaStream_t stream) {
+  using Cfg = WgCfg<NW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(umma_wgrad_mn_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
+      return NERO_ERR_CUDA;
+    attr_set = true;
+  }
+  umma_wgrad_mn_kernel<NW><<<dim3(P, n_tiles), kWgThreads, Cfg::smem_bytes, stream>>>(p);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
 template <int NW>
 static int launch_wgrad(const WgradParams& p, int P, int n_tiles, cudaStream_t stream) {
   using Cfg = WgCfg<NW>;
@@ -241,14 +440,18 @@ int wgrad_dispatch(WgradParams p, int n_rows_pad, int k_pad, int P, cudaStream_t
   if ((p.ld_partial & 3) || k_pad % 64 || n_rows_pad % 16 || P <= 0) return NERO_ERR_ARG;
   const int n_tiles = (n_rows_pad + 127) / 128;
   p.n0 = 0;
+  // the MN-major kernel copies rows with 16-byte loads: needs 16-byte aligned rows and column origins
+  auto al = [](const float* q, int ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld & 3) == 0); };
+  static const int mn_env = [] { const char* e = getenv("NERO_WGRAD_MN"); return e ? atoi(e) : 1; }();
+  const bool mn = mn_env != 0 && al(p.dY, p.ldy) && al(p.X, p.ldx) && al(p.dY2, p.ldy2) && al(p.X2, p.ldx2);
   int k0 = 0;
   while (k0 < k_pad) {
     const int rem = k_pad - k0;
     p.k0 = k0;
     int rc;
-    if (rem >= 256) { rc = launch_wgrad<256>(p, P, n_tiles, stream); k0 += 256; }
-    else if (rem >= 128) { rc = launch_wgrad<128>(p, P, n_tiles, stream); k0 += 128; }
-    else { rc = launch_wgrad<64>(p, P, n_tiles, stream); k0 += 64; }
+    if (rem >= 256) { rc = mn ? launch_wgrad_mn<256>(p, P, n_tiles, stream) : launch_wgrad<256>(p, P, n_tiles, stream); k0 += 256; }
+    else if (rem >= 128) { rc = mn ? launch_wgrad_mn<128>(p, P, n_tiles, stream) : launch_wgrad<128>(p, P, n_tiles, stream); k0 += 128; }
+    else { rc = mn ? launch_wgrad_mn<64>(p, P, n_tiles, stream) : launch_wgrad<64>(p, P, n_tiles, stream); k0 += 64; }
     if (rc != NERO_OK) return rc;
   }
   return NERO_OK;

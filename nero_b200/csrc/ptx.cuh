@@ -127,6 +127,18 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile, 128-byte swizzle (cute::UMMA canonical layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in bf16
+// elements): an atom is 8 K-rows x 64 MN-elements (8 x 128 B, 16-byte chunks XOR-swizzled with the row index); atoms
+// repeat along K every `sbo` bytes and along MN every `lbo` bytes.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  return d;
+}
 // kind::f16 instruction descriptor: BF16 x BF16 -> F32, both operands K-major, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)                 // c_format  = F32
@@ -134,6 +146,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
          | (1u << 10)              // b_format  = BF16
          | ((N >> 3) << 17)        // n_dim
          | ((M >> 4) << 24);       // m_dim
+}
+// same with both operands MN-major (a_major bit 15, b_major bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(uint32_t M, uint32_t N) {
+  return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 }  // namespace nero
