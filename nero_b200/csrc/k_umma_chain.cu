@@ -190,6 +190,174 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Epilogue v2: accumulator fragments in the 16x256b TMEM load shape (thread t of a warp holds, per 8-column repeat,
+// columns 2(t%4), 2(t%4)+1 of rows t/4 and t/4+8 -- the m16n8 fragment).  A quad then covers 32 contiguous bytes of one
+// matrix row, so aux operands (H, addend, V) are read and results written DIRECTLY from/to global memory with full
+// 32-byte sectors: no shared-memory transposes, no warp syncs, and the loads are in flight before the accumulator
+// read completes.  The packed split-bf16 A operand of the next layer is one 32-bit word per (row, column pair) = the
+// 16x128b store shape with the same thread <-> (row, column) map.
+#ifndef NERO_EPI_V2
+#define NERO_EPI_V2 1
+#endif
+
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// element e = 4j + 2hh + q of a [16 rows x 32 cols] unit  <->  row rlo + 8hh, column c0 + 8j + 2a + q
+struct FragPos { int rlo; int a; bool plo, phi; };
+
+__device__ __forceinline__ bool vec2_ok(const float* p, int ld) {
+  return ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
+}
+// g: matrix origin (row 0, first column of the layer window); columns >= ncols and masked rows read as zero
+__device__ __forceinline__ void frag_load(const float* __restrict__ g, int ld, const FragPos& f, int c0, int ncols, bool v2, float* x) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = c0 + 8 * j + 2 * f.a;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float2 val = make_float2(0.f, 0.f);
+      if ((hh ? f.phi : f.plo) && col < ncols) {
+        const float* p = g + size_t(f.rlo + 8 * hh) * ld + col;
+        if (v2 && col + 1 < ncols) val = *reinterpret_cast<const float2*>(p);
+        else { val.x = p[0]; if (col + 1 < ncols) val.y = p[1]; }
+      }
+      x[4 * j + 2 * hh] = val.x; x[4 * j + 2 * hh + 1] = val.y;
+    }
+  }
+}
+__device__ __forceinline__ void frag_store(float* __restrict__ g, int ld, const FragPos& f, int c0, int ncols, bool v2, const float* x) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = c0 + 8 * j + 2 * f.a;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if ((hh ? f.phi : f.plo) && col < ncols) {
+        float* p = g + size_t(f.rlo + 8 * hh) * ld + col;
+        if (v2 && col + 1 < ncols) *reinterpret_cast<float2*>(p) = make_float2(x[4 * j + 2 * hh], x[4 * j + 2 * hh + 1]);
+        else { p[0] = x[4 * j + 2 * hh]; if (col + 1 < ncols) p[1] = x[4 * j + 2 * hh + 1]; }
+      }
+    }
+  }
+}
+// next layer's A operand: 32 columns of this unit as packed split-bf16 (16 packed columns per plane)
+__device__ __forceinline__ void frag_write_a(uint32_t tl, int c0, const float* r) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    split2(r[4 * j], r[4 * j + 1], hi[2 * j], lo[2 * j]);              // row t/4
+    split2(r[4 * j + 2], r[4 * j + 3], hi[2 * j + 1], lo[2 * j + 1]);  // row t/4 + 8
+  }
+  tmem_st_16x128b_x4(tl + kAHiCol + (c0 >> 1), hi);
+  tmem_st_16x128b_x4(tl + kALoCol + (c0 >> 1), lo);
+}
+
+template <int KIND>
+__device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint32_t tmem_base, int lg, int grp_row0, int rows_valid,
+                                                      int third, int lane, const float* s_bias) {
+  constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
+  const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
+  const int ncols_a = L.write_a ? max(L.a_blocks * 16, L.n_pad) : 0;     // columns of the next A operand to define
+  const int n_units = ((max(L.n_pad, ncols_a) + 31) >> 5) * 2;
+  const bool v2_save = L.save && vec2_ok(L.save, L.ld_save);
+#pragma unroll 1
+  for (int u = third; u < n_units; u += 3) {
+    const int h = u & 1, c0 = (u >> 1) * 32;
+    const int rl = h * 16 + (lane >> 2);
+    FragPos f;
+    f.rlo = grp_row0 + rl; f.a = lane & 3; f.plo = rl < rows_valid; f.phi = rl + 8 < rows_valid;
+    const uint32_t tl = tmem_base + (uint32_t(lg * 32 + h * 16) << 16);
+    float r[16];
+    if (c0 < L.ncol_out) {
+      float v[16];
+      if constexpr (kBias) {
+        tmem_ld_16x256b_x4(tl + kAccCol + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 b = *reinterpret_cast<const float2*>(s_bias + ((c0 + 8 * j + 2 * f.a) & 255));
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.x; v[4 * j + 3] += b.y;
+        }
+        if constexpr (KIND == EK_BIAS_SOFTPLUS) softplus100_fast16(v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float y = v[e];
+          if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
+          else if constexpr (KIND == EK_BIAS_GENERIC) y = apply_act(y, L.act, L.act_param);
+          r[e] = L.oscale * y;
+        }
+      } else {
+        float s[16];
+        if constexpr (KIND != EK_DACT_NONE) frag_load(L.H, L.ldh, f, c0, nmain, vec2_ok(L.H, L.ldh), s);   // in flight during the TMEM read
+        tmem_ld_16x256b_x4(tl + kAccCol + c0, v);
+        tmem_ld_wait();
+        if constexpr (KIND == EK_DACT_NONE) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) s[e] = 1.0f;
+        } else if constexpr (KIND == EK_DACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) s[e] = s[e] > 0.0f ? 1.0f : 0.0f;
+        } else {
+          dsoftplus100_from_h_fast16(s, L.hscale);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = L.oscale * s[e] * v[e];
+        if (L.addend) {
+          float ad[16];
+          frag_load(L.addend, L.ldadd, f, c0, nmain, vec2_ok(L.addend, L.ldadd), ad);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] += ad[e];
+        }
+        if (L.tail && c0 + 32 > L.ncol_main) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int col = c0 + 8 * (e >> 2) + 2 * f.a + (e & 1);
+            const bool pr = (e & 2) ? f.phi : f.plo;
+            if (pr && col >= L.ncol_main && col < L.ncol_out)
+              L.tail[size_t(f.rlo + ((e & 2) ? 8 : 0)) * L.ldt + (col - L.ncol_main)] = L.oscale * v[e];
+          }
+        }
+        if constexpr (KIND == EK_TANGENT) {
+          float vv[16];
+          frag_load(L.V, L.ldv, f, c0, nmain, vec2_ok(L.V, L.ldv), vv);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) vv[e] = 100.0f * (1.0f - s[e]) * vv[e] * v[e];
+          frag_store(L.out2, L.ldo2, f, c0, nmain, vec2_ok(L.out2, L.ldo2), vv);
+        }
+      }
+      if (L.save) frag_store(L.save, L.ld_save, f, c0, nmain, v2_save, r);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = 0.0f;
+    }
+    if (c0 < ncols_a) {
+      if (c0 + 32 > nmain) {   // columns >= nmain: the skip-concat source (from the save buffer) or zero
+        float cc[16];
+        if (L.csrc) frag_load(L.csrc, L.ld_csrc, f, c0, 256, vec2_ok(L.csrc, L.ld_csrc), cc);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c0 + 8 * (e >> 2) + 2 * f.a + (e & 1);
+          if (col >= nmain) r[e] = L.csrc ? cc[e] : 0.0f;
+        }
+      }
+      frag_write_a(tl, c0, r);
+    }
+  }
+}
+
 // FAM: 0 = bias/activation epilogues (forward chains), 1 = derivative-product epilogues (gradient sweeps), 2 = tangent
 // sweep.  One instantiation per family keeps the register pressure of each kernel low enough for ptxas to overlap
 // the sixteen independent MUFU chains of a block instead of serialising them through one register.
@@ -234,6 +402,19 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
       const int rows_valid = min(32, M - row0);
       // ---- first A operand: fp32 rows from HBM -> split-bf16 in TMEM
       {
+#if NERO_EPI_V2
+        const bool v0 = vec2_ok(p.A0, p.lda0);
+        const int nu0 = p.L[0].k_chunks * 4;      // [16 x 32] units: every column the first layer's MMAs read (zeros beyond k_valid0)
+        for (int u = third; u < nu0; u += 3) {
+          const int h = u & 1, c0 = (u >> 1) * 32;
+          const int rl = h * 16 + (lane >> 2);
+          FragPos f;
+          f.rlo = row0 + rl; f.a = lane & 3; f.plo = rl < rows_valid; f.phi = rl + 8 < rows_valid;
+          float x[16];
+          frag_load(p.A0, p.lda0, f, c0, p.k_valid0, v0, x);
+          frag_write_a(tmem_base + (uint32_t(lg * 32 + h * 16) << 16), c0, x);
+        }
+#else
         const bool v0 = vec_ok(p.A0, p.lda0);
         const int nb0 = p.L[0].k_chunks * 4;      // every column the first layer's MMAs read (zeros beyond k_valid0)
         for (int b = third; b < nb0; b += 3) {
@@ -241,6 +422,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           load_block16(p.A0 + size_t(row0) * p.lda0 + b * 16, p.lda0, rows_valid, p.k_valid0 - b * 16, v0, stg, lane, x);
           write_a16(tl, b * 16, x);
         }
+#endif
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -266,17 +448,23 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         acc_phase ^= 1;
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
+#if NERO_EPI_V2
+#define NERO_EPI_CALL(K) chain_epilogue_layer2<K>(L, tmem_base, lg, row0, rows_valid, third, lane, sb)
+#else
+#define NERO_EPI_CALL(K) chain_epilogue_layer<K>(L, tl, row0, rows_valid, third, lane, stg, sb)
+#endif
         if constexpr (FAM == 0) {
-          if (L.kind == EK_BIAS_SOFTPLUS) chain_epilogue_layer<EK_BIAS_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb);
-          else if (L.kind == EK_BIAS_RELU) chain_epilogue_layer<EK_BIAS_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb);
-          else chain_epilogue_layer<EK_BIAS_GENERIC>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
+          else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
+          else NERO_EPI_CALL(EK_BIAS_GENERIC);
         } else if constexpr (FAM == 1) {
-          if (L.kind == EK_DACT_SOFTPLUS) chain_epilogue_layer<EK_DACT_SOFTPLUS>(L, tl, row0, rows_valid, third, lane, stg, sb);
-          else if (L.kind == EK_DACT_RELU) chain_epilogue_layer<EK_DACT_RELU>(L, tl, row0, rows_valid, third, lane, stg, sb);
-          else chain_epilogue_layer<EK_DACT_NONE>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          if (L.kind == EK_DACT_SOFTPLUS) NERO_EPI_CALL(EK_DACT_SOFTPLUS);
+          else if (L.kind == EK_DACT_RELU) NERO_EPI_CALL(EK_DACT_RELU);
+          else NERO_EPI_CALL(EK_DACT_NONE);
         } else {
-          chain_epilogue_layer<EK_TANGENT>(L, tl, row0, rows_valid, third, lane, stg, sb);
+          NERO_EPI_CALL(EK_TANGENT);
         }
+#undef NERO_EPI_CALL
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
