@@ -48,8 +48,23 @@ constexpr int CH_BM = 128, CH_BK = 64;
 constexpr int kChEpiWarps = 12;
 constexpr int kChMmaWarp = kChEpiWarps, kChLoadWarp = kChEpiWarps + 1;
 constexpr int kChThreads = (kChEpiWarps + 2) * 32;
+#ifndef NERO_EPI_V2
+#define NERO_EPI_V2 1
+#endif
+// NERO_NSPLIT=1 (needs the v2 epilogue): layers wider than 128 columns run as two N halves so that the epilogue of half 0
+// overlaps the MMAs of half 1.  Measured on B200 (round 1): 15.6 -> 16.0-16.5 ms/step, i.e. a LOSS -- the epilogue of half
+// 0 may not overwrite the A operand in TMEM before the half-1 MMAs have read it (a_free barrier), N=128 MMAs have less
+// reuse of the A operand, and the epilogue, not the MMA, is the longer phase.  Kept for experiments, off by default.
+#ifndef NERO_NSPLIT
+#define NERO_NSPLIT 0
+#endif
+#if NERO_NSPLIT
+constexpr int kChStages = 6;
+constexpr uint32_t kChStageBytes = 2 * 128 * 128;                       // half a W chunk: hi + lo planes of up to 128 rows
+#else
 constexpr int kChStages = 3;
 constexpr uint32_t kChStageBytes = 2 * 256 * 128;                       // W chunk: hi + lo planes of up to 256 rows
+#endif
 constexpr uint32_t kChEpiBytes = kChEpiWarps * kStageWarpBytes;         // 30 KB
 constexpr uint32_t kChBiasBytes = 2 * 256 * 4;
 constexpr uint32_t kChSmemBytes = kChStages * kChStageBytes + kChEpiBytes + kChBiasBytes + 1024 + 256;
@@ -267,7 +282,7 @@ __device__ __forceinline__ void frag_write_a(uint32_t tl, int c0, const float* r
 
 template <int KIND>
 __device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint32_t tmem_base, int lg, int grp_row0, int rows_valid,
-                                                      int third, int lane, const float* s_bias) {
+                                                      int third, int lane, const float* s_bias, uint64_t* acc_ready1, uint64_t* a_free, uint32_t phase1) {
   constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
   const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
   const int ncols_a = L.write_a ? max(L.a_blocks * 16, L.n_pad) : 0;     // columns of the next A operand to define
@@ -276,6 +291,11 @@ __device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint3
 #pragma unroll 1
   for (int u = third; u < n_units; u += 3) {
     const int h = u & 1, c0 = (u >> 1) * 32;
+    if (acc_ready1 && c0 >= 128) {      // second N half of the accumulator: its MMAs ran while half 0 was processed
+      mbar_wait(acc_ready1, phase1);
+      tcgen05_fence_after();
+      acc_ready1 = nullptr;
+    }
     const int rl = h * 16 + (lane >> 2);
     FragPos f;
     f.rlo = grp_row0 + rl; f.a = lane & 3; f.plo = rl < rows_valid; f.phi = rl + 8 < rows_valid;
@@ -353,6 +373,13 @@ __device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint3
           if (col >= nmain) r[e] = L.csrc ? cc[e] : 0.0f;
         }
       }
+      // two-halves layers: the half-1 MMAs of THIS layer still read K < 128 of the current A operand while half 0 is
+      // processed; its first k-chunks retire long before the first unit gets here, but the order must not rest on timing
+      if (a_free && c0 < 128) {
+        mbar_wait(a_free, phase1);
+        tcgen05_fence_after();
+        a_free = nullptr;
+      }
       frag_write_a(tl, c0, r);
     }
   }
@@ -371,8 +398,9 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   uint64_t* full = bars;                        // [stages]  W chunk landed
   uint64_t* empty = bars + kChStages;           // [stages]  W chunk consumed
   uint64_t* a_ready = bars + 2 * kChStages;     // A operand written + accumulator drained (12 epilogue warps)
-  uint64_t* acc_ready = bars + 2 * kChStages + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kChStages + 2);
+  uint64_t* acc_ready = bars + 2 * kChStages + 1;   // [2]: accumulator columns of N half 0 / half 1 complete
+  uint64_t* a_free = bars + 2 * kChStages + 3;      // half-1 MMAs are done reading K < 128 of the current A operand
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kChStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int M = p.m_ptr ? *p.m_ptr : p.m_cap;
@@ -383,6 +411,8 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     for (int s = 0; s < kChStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_ready, kChEpiWarps);
     mbar_init(acc_ready, 1);
+    mbar_init(acc_ready + 1, 1);
+    mbar_init(a_free, 1);
     fence_mbar_init();
   }
   if (warp == kChLoadWarp) tmem_alloc<512>(tmem_slot);
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     const int lg = warp & 3, third = warp >> 2;
     float* stg = s_epi + warp * (32 * kStagePitch);
     const uint32_t tl = tmem_base + (uint32_t(lg * 32) << 16);
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, acc_phase1 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int row0 = tile * CH_BM + lg * 32;
       const int rows_valid = min(32, M - row0);
@@ -444,12 +474,13 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           const int i = warp * 32 + lane;
           sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
         }
+        const bool two_halves = NERO_NSPLIT && L.n_pad > 128;
         mbar_wait(acc_ready, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
 #if NERO_EPI_V2
-#define NERO_EPI_CALL(K) chain_epilogue_layer2<K>(L, tmem_base, lg, row0, rows_valid, third, lane, sb)
+#define NERO_EPI_CALL(K) chain_epilogue_layer2<K>(L, tmem_base, lg, row0, rows_valid, third, lane, sb, two_halves ? acc_ready + 1 : nullptr, two_halves ? a_free : nullptr, acc_phase1)
 #else
 #define NERO_EPI_CALL(K) chain_epilogue_layer<K>(L, tl, row0, rows_valid, third, lane, stg, sb)
 #endif
@@ -465,6 +496,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           NERO_EPI_CALL(EK_TANGENT);
         }
 #undef NERO_EPI_CALL
+        if (two_halves) acc_phase1 ^= 1;
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -479,30 +511,36 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int l = 0; l < p.n_layers; ++l) {
         const ChainLayer& L = p.L[l];
-        const uint32_t idesc = make_idesc_bf16(CH_BM, uint32_t(L.n_pad));
-        const uint32_t b_plane = uint32_t(L.n_pad) * 128u;
+        const int nh = (NERO_NSPLIT && L.n_pad > 128) ? 2 : 1;
+        const uint32_t half_rows = uint32_t(L.n_pad) / nh;
+        const uint32_t idesc = make_idesc_bf16(CH_BM, half_rows);
+        const uint32_t b_plane = half_rows * 128u;
         mbar_wait(a_ready, a_phase);
         a_phase ^= 1;
         tcgen05_fence_after();
-        for (int c = 0; c < L.k_chunks; ++c, ++g) {
-          const int s = g % kChStages;
-          mbar_wait(&full[s], (g / kChStages) & 1);
-          tcgen05_fence_after();
-          if (elect_one()) {
-            const uint32_t b_hi = smem_u32(smem + s * kChStageBytes);
-            const uint32_t b_lo = b_hi + b_plane;
+        for (int hf = 0; hf < nh; ++hf) {
+          const uint32_t d_col = tmem_base + kAccCol + uint32_t(hf) * half_rows;
+          for (int c = 0; c < L.k_chunks; ++c, ++g) {
+            const int s = g % kChStages;
+            mbar_wait(&full[s], (g / kChStages) & 1);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t b_hi = smem_u32(smem + s * kChStageBytes);
+              const uint32_t b_lo = b_hi + b_plane;
 #pragma unroll
-            for (int k = 0; k < CH_BK / 16; ++k) {
-              const uint32_t a_col = uint32_t(c * 32 + k * 8);
-              const uint64_t dbh = make_desc_k_sw128(b_hi + k * 32), dbl = make_desc_k_sw128(b_lo + k * 32);
-              umma_bf16_ts(tmem_base + kAccCol, tmem_base + kALoCol + a_col, dbh, idesc, (c | k) != 0);
-              umma_bf16_ts(tmem_base + kAccCol, tmem_base + kAHiCol + a_col, dbl, idesc, 1);
-              umma_bf16_ts(tmem_base + kAccCol, tmem_base + kAHiCol + a_col, dbh, idesc, 1);
+              for (int k = 0; k < CH_BK / 16; ++k) {
+                const uint32_t a_col = uint32_t(c * 32 + k * 8);
+                const uint64_t dbh = make_desc_k_sw128(b_hi + k * 32), dbl = make_desc_k_sw128(b_lo + k * 32);
+                umma_bf16_ts(d_col, tmem_base + kALoCol + a_col, dbh, idesc, (c | k) != 0);
+                umma_bf16_ts(d_col, tmem_base + kAHiCol + a_col, dbl, idesc, 1);
+                umma_bf16_ts(d_col, tmem_base + kAHiCol + a_col, dbh, idesc, 1);
+              }
+              umma_commit(&empty[s]);
+              if (nh == 2 && hf == 1 && c == min(L.k_chunks, 2) - 1) umma_commit(a_free);   // K < 128 of A no longer needed
+              if (c == L.k_chunks - 1) umma_commit(acc_ready + hf);
             }
-            umma_commit(&empty[s]);
-            if (c == L.k_chunks - 1) umma_commit(acc_ready);
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -512,15 +550,22 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int l = 0; l < p.n_layers; ++l) {
         const ChainLayer& L = p.L[l];
-        const uint32_t bytes = 2u * uint32_t(L.n_pad) * 128u;
-        for (int c = 0; c < L.k_chunks; ++c, ++g) {
-          const int s = g % kChStages;
-          mbar_wait(&empty[s], ((g / kChStages) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_copy_g2s(smem + s * kChStageBytes, L.wimg + size_t(c) * bytes, bytes, &full[s]);
+        const int nh = (NERO_NSPLIT && L.n_pad > 128) ? 2 : 1;
+        const uint32_t half_rows = uint32_t(L.n_pad) / nh;
+        const uint32_t plane = uint32_t(L.n_pad) * 128u, hp = half_rows * 128u;
+        for (int hf = 0; hf < nh; ++hf) {
+          for (int c = 0; c < L.k_chunks; ++c, ++g) {
+            const int s = g % kChStages;
+            mbar_wait(&empty[s], ((g / kChStages) & 1) ^ 1);
+            if (elect_one()) {
+              // rows [hf*half_rows, +half_rows) of the chunk's hi plane and of its lo plane
+              const uint8_t* src = L.wimg + size_t(c) * 2u * plane + size_t(hf) * hp;
+              mbar_arrive_expect_tx(&full[s], 2u * hp);
+              bulk_copy_g2s(smem + s * kChStageBytes, src, hp, &full[s]);
+              bulk_copy_g2s(smem + s * kChStageBytes + hp, src + plane, hp, &full[s]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
