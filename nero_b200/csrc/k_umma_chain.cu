@@ -317,7 +317,11 @@ __device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint3
           float y = v[e];
           if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
           else if constexpr (KIND == EK_BIAS_GENERIC) y = apply_act(y, L.act, L.act_param);
-          r[e] = L.oscale * y;
+          r[e] = y;
+        }
+        if (L.oscale != 1.0f) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] *= L.oscale;
         }
       } else {
         float s[16];
@@ -334,7 +338,11 @@ __device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint3
           dsoftplus100_from_h_fast16(s, L.hscale);
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = L.oscale * s[e] * v[e];
+        for (int e = 0; e < 16; ++e) r[e] = s[e] * v[e];
+        if (L.oscale != 1.0f) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] *= L.oscale;
+        }
         if (L.addend) {
           float ad[16];
           frag_load(L.addend, L.ldadd, f, c0, nmain, vec2_ok(L.addend, L.ldadd), ad);

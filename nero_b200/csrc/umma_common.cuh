@@ -46,8 +46,10 @@ __device__ __forceinline__ void softplus100_fast16(float* x) {
   for (int j = 0; j < 16; ++j) t[j] = ex2_ftz(fminf(x[j], 0.2f) * (100.0f * 1.4426950408889634f));
 #pragma unroll
   for (int j = 0; j < 16; ++j) t[j] = lg2_ftz(1.0f + t[j]);
+  // softplus(x) >= x everywhere and the clamped branch saturates at softplus(0.2) = 0.2 + 2e-11, so the select
+  // "x > 0.2 ? x : ..." is a plain max (one FMNMX instead of FSETP + FSEL)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = (x[j] > 0.2f) ? x[j] : t[j] * (0.6931471805599453f * 0.01f);
+  for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], t[j] * (0.6931471805599453f * 0.01f));
 }
 // sigma(100 a) from h = softplus(a) (possibly stored scaled by 1/hscale): 1 - 2^(-100*log2e*hscale*h); for
 // 100*hscale*h > 20 the exponential is < 2.1e-9, below fp32 resolution of 1 - t, so no branch is needed
