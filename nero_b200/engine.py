@@ -691,7 +691,9 @@ class ShapeEngine:
         sel = w['SEL']
         if cnt > maxp:   # renderer.py:535-541 random subset
             idx = perm if perm is not None else torch.randperm(cnt, device=self.dev)
-            sel = sel[:cnt][idx[:maxp].to(self.dev)].contiguous()
+            # the compaction kernel orders candidates only within a block; the reference indexes them in sample order
+            # (boolean-mask gather), so restore that order before the permutation picks its subset
+            sel = torch.sort(sel[:cnt])[0][idx[:maxp].to(self.dev)].contiguous()
             cnt = maxp
             w['SEL_SUB'] = sel
         P = cnt
