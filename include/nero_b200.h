@@ -216,6 +216,11 @@ int nero_mc_dir_bwd(const nero_mc_params* q, void* stream);
 /* MaterialFeatsNetwork inputs (field.py:660-689): PE8 rows, skip-concat tail, xyz for the predictor input */
 int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, void* stream);
 
+/* Adam step over one flat fp32 parameter buffer (torch.optim.Adam semantics; replaces the multi-tensor optimizer launch of
+ * train/trainer.py:73-76,160-166).  lr_over_bc1 = lr / (1 - b1^t), inv_sqrt_bc2 = 1 / sqrt(1 - b2^t); buffers 16-byte aligned. */
+int nero_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr_over_bc1, float b1, float b2, float eps,
+                   float inv_sqrt_bc2, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,4 +179,46 @@ int colsum(const float* X, int ldx, int ncol, const float* w, int ldw, const int
   return NERO_OK;
 }
 
+
+// Adam over ONE flat fp32 parameter buffer (torch.optim.Adam semantics, amsgrad=False, maximize=False):
+//   g += wd * p;  m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g g;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// bc1 = 1 - b1^t, bc2 = 1 - b2^t are computed on the host.  Replaces the multi-tensor optimizer launch over the ~140
+// small parameter tensors of a NeRO stage (train/trainer.py:73-76, 160-166) with one pass over 2.2 M floats.
+__global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 long n, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2, float wd) {
+  const long i4 = (long(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 3 < n) {
+    float4 P = *reinterpret_cast<float4*>(p + i4), M = *reinterpret_cast<float4*>(m + i4), V = *reinterpret_cast<float4*>(v + i4);
+    const float4 G = *reinterpret_cast<const float4*>(g + i4);
+    float* pp = reinterpret_cast<float*>(&P); float* mm = reinterpret_cast<float*>(&M); float* vv = reinterpret_cast<float*>(&V);
+    const float* gg = reinterpret_cast<const float*>(&G);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = gg[j] + wd * pp[j];
+      mm[j] = mm[j] + (gr - mm[j]) * (1.0f - b1);
+      vv[j] = vv[j] * b2 + (1.0f - b2) * gr * gr;
+      pp[j] -= lr_over_bc1 * (mm[j] / (sqrtf(vv[j]) * inv_sqrt_bc2 + eps));
+    }
+    *reinterpret_cast<float4*>(p + i4) = P; *reinterpret_cast<float4*>(m + i4) = M; *reinterpret_cast<float4*>(v + i4) = V;
+  } else {
+    for (long i = i4; i < n; ++i) {
+      const float gr = g[i] + wd * p[i];
+      m[i] = m[i] + (gr - m[i]) * (1.0f - b1);
+      v[i] = v[i] * b2 + (1.0f - b2) * gr * gr;
+      p[i] -= lr_over_bc1 * (m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps));
+    }
+  }
+}
+int adam_flat(float* p, const float* g, float* m, float* v, long n, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2,
+              float wd, cudaStream_t st) {
+  if (n <= 0) return NERO_OK;
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15)
+    return NERO_ERR_ARG;
+  const long n4 = (n + 3) / 4;
+  adam_flat_kernel<<<int((n4 + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, wd);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
 }  // namespace nero

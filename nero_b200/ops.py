@@ -301,6 +301,8 @@ def K(name, *args):
             conv.append(a.ptr())
         elif isinstance(a, float):
             conv.append(ctypes.c_float(a))
+        elif isinstance(a, ctypes._SimpleCData):
+            conv.append(a)
         else:
             conv.append(int(a))
     if DRY_RUN:

@@ -180,3 +180,37 @@ def test_chain_matches_layerwise_and_fp64():
         e = float((got.double() - want).abs().max())
         print(f'chain dact {nm}: max abs err {e:.2e} (|want| max {float(want.abs().max()):.2e})')
         assert e < 3e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_flat_adam_matches_torch_adam():
+    """nero_adam_flat over the flat parameter buffer vs torch.optim.Adam on the same gradients (train/trainer.py:73-76)."""
+    import nero_oracle as O
+    from helpers import build_params
+    from nero_b200.renderer import NeROShapeRenderer
+    from nero_b200.optim import FlatAdam
+    cfg = {'n_samples': 32, 'n_importance': 32}
+    net = NeROShapeRenderer(cfg, training=False)
+    net.load_state_dict(build_params(cfg))
+    net = net.cuda()
+    ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+    opt_ref = torch.optim.Adam(ref, lr=5e-4)
+    opt = FlatAdam(net, lr=5e-4)
+    r = {k: v.cuda() for k, v in O.synthetic_rays(32, seed=6033).items()}
+    for it in range(3):
+        opt.zero_grad()
+        out = net.render(r['rays_o'], r['rays_d'], r['near'], r['far'], r['human_poses'], 0, 1.0, True, 30000)
+        (torch.mean(net.compute_rgb_loss(out['ray_rgb'], r['rgb'])) + torch.mean(out['gradient_error'] * 0.1)).backward()
+        for q, p in zip(ref, net.parameters()):
+            q.grad = p.grad.detach().clone()
+        opt.param_groups[0]['lr'] = opt_ref.param_groups[0]['lr'] = 5e-4 * (it + 1)      # the trainer sets the lr every step
+        opt.step()
+        opt_ref.step()
+        for q, p in zip(ref, net.parameters()):
+            assert float((q - p).abs().max()) <= 1e-6 * float(q.abs().max()) + 1e-9
+    sd = opt.state_dict()
+    assert len(sd['state']) == len(ref) and int(float(sd['state'][0]['step'])) == 3
+    fresh = torch.optim.Adam([q.detach().clone().requires_grad_(True) for q in ref], lr=1e-3)
+    fresh.load_state_dict(sd)                                   # interchangeable with torch's optimizer checkpoints
+    opt2 = FlatAdam(net, lr=1e-3)
+    opt2.load_state_dict(opt_ref.state_dict())
+    assert opt2.t == 3 and float((opt2.exp_avg - opt.exp_avg).abs().max()) <= 1e-7

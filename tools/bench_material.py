@@ -57,7 +57,9 @@ def main():
     assert idx.shape[0] == P
     batch = {'pts': inters[idx].contiguous(), 'rays_d': rays['rays_d'].to(dev)[idx].contiguous(), 'normals': normals[idx].contiguous(),
              'rgb': rays['rgb'].to(dev)[idx].contiguous(), 'human_poses': rays['human_poses'].to(dev)[idx].contiguous()}
-    opt = torch.optim.Adam(net.parameters(), lr=5e-4, fused=True)
+    from nero_b200.optim import FlatAdam
+    _ = net.engine
+    opt = FlatAdam(net, lr=5e-4)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -122,7 +124,7 @@ def main():
             'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'data': 'synthetic',
             'dtype': 'f32 (split-bf16 x3 tensor-core MMAs, fp32 accumulate)',
             'config': {'workload': f'bell_material_{P}pts_x_(512+256)dirs', 'triangles': int(tris.shape[0]), 'secondary_rays': N,
-                       'rays_hit': n_hit, 'rays_miss': n_miss, 'bvh_build_s': t_bvh, 'optimizer': 'torch Adam(fused) inside the timed region'},
+                       'rays_hit': n_hit, 'rays_miss': n_miss, 'bvh_build_s': t_bvh, 'optimizer': 'Adam (nero_adam_flat) inside the timed region'},
             'secondary_rays_per_s': N / (ms * 1e-3), 'gpu_launches': launches,
             'phases': phases, 'trace': {'ms': trace_ms, 'rays_per_s': N / (trace_ms * 1e-3)},
             'step_tensor_tflops': flops / (ms * 1e-3) / 1e12, 'cpu_baseline': None}
