@@ -73,7 +73,7 @@ int prep_weight(const float* v, const float* g, int K, int row0, int nrows, cons
 
 // one block per layer row n = row0 + blockIdx.x; blockDim = (kcols, 4): the P split-K partials are summed by 4 thread
 // groups in parallel (the per-row reads are latency bound), then reduced through shared memory.
-__global__ void __launch_bounds__(1024) wgrad_finish_kernel(const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
+__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
                                     const float* __restrict__ bias_partial, int K, int row0,
                                     const int* __restrict__ kmap, float in_scale, const float* __restrict__ v,
                                     const float* __restrict__ g, float* grad_w, float* grad_g, float* grad_b,
@@ -86,23 +86,14 @@ __global__ void __launch_bounds__(1024) wgrad_finish_kernel(const float* __restr
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const int kc = kmap ? kmap[k] : k;
     const float* pp = partial + size_t(r) * ld_partial + kc;
-    // the reads are pure latency (one 4-byte load per partial): issue 10 independent loads per pass, then add
-    // them in a fixed tree order (deterministic)
-    float tot = 0.f;
-    for (int p0 = threadIdx.y; p0 < P; p0 += 40) {
-      float a[10];
-#pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int pidx = p0 + 4 * i;
-        a[i] = pidx < P ? __ldg(pp + size_t(pidx) * pstride) : 0.f;
-      }
-#pragma unroll
-      for (int w = 1; w < 10; w <<= 1)
-#pragma unroll
-        for (int i = 0; i + w < 10; i += 2 * w) a[i] += a[i + w];
-      tot += a[0];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int pidx = threadIdx.y;
+    for (; pidx + 12 < P; pidx += 16) {
+      a0 += pp[size_t(pidx) * pstride]; a1 += pp[size_t(pidx + 4) * pstride];
+      a2 += pp[size_t(pidx + 8) * pstride]; a3 += pp[size_t(pidx + 12) * pstride];
     }
-    s_dw[threadIdx.y * K + k] = tot;
+    for (; pidx < P; pidx += 4) a0 += pp[size_t(pidx) * pstride];
+    s_dw[threadIdx.y * K + k] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   for (int k = tid; k < K; k += nthreads) {
