@@ -216,6 +216,12 @@ int nero_mc_dir_bwd(const nero_mc_params* q, void* stream);
 /* MaterialFeatsNetwork inputs (field.py:660-689): PE8 rows, skip-concat tail, xyz for the predictor input */
 int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, void* stream);
 
+/* nero_wgrad_finish for many layers in ONE launch.  jobs_dev: device array of n_jobs records
+ *   { const float* partial, *bias_partial; const int* kmap; const float* v, *g; float* grad_w, *grad_g, *grad_b;
+ *     const float* extra_row; int P, rows_partial, ld_partial, K, row0, nrows; float in_scale, extra_scale; }
+ * (same meaning as the nero_wgrad_finish arguments; 104 bytes each).  Jobs of one launch must not share destination rows. */
+int nero_wgrad_finish_batch(const void* jobs_dev, int n_jobs, int max_rows, int max_k, void* stream);
+
 /* Adam step over one flat fp32 parameter buffer (torch.optim.Adam semantics; replaces the multi-tensor optimizer launch of
  * train/trainer.py:73-76,160-166).  lr_over_bc1 = lr / (1 - b1^t), inv_sqrt_bc2 = 1 / sqrt(1 - b2^t); buffers 16-byte aligned. */
 int nero_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr_over_bc1, float b1, float b2, float eps,

@@ -73,14 +73,14 @@ int prep_weight(const float* v, const float* g, int K, int row0, int nrows, cons
 
 // one block per layer row n = row0 + blockIdx.x; blockDim = (kcols, 4): the P split-K partials are summed by 4 thread
 // groups in parallel (the per-row reads are latency bound), then reduced through shared memory.
-__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
+__device__ __forceinline__ void wgrad_finish_row(int r, const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
                                     const float* __restrict__ bias_partial, int K, int row0,
                                     const int* __restrict__ kmap, float in_scale, const float* __restrict__ v,
                                     const float* __restrict__ g, float* grad_w, float* grad_g, float* grad_b,
                                     const float* __restrict__ extra_row, float extra_scale) {
   __shared__ float sh[32];
   extern __shared__ float s_dw[];  // [4][K] partial sums, then [K] in slot 0
-  const int r = blockIdx.x, n = row0 + r;
+  const int n = row0 + r;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
   const size_t pstride = size_t(rows_partial) * ld_partial;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -123,6 +123,35 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, in
   } else {
     for (int k = tid; k < K; k += nthreads) grad_w[size_t(n) * K + k] += s_dw[k];
   }
+}
+
+__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
+                                    const float* __restrict__ bias_partial, int K, int row0,
+                                    const int* __restrict__ kmap, float in_scale, const float* __restrict__ v,
+                                    const float* __restrict__ g, float* grad_w, float* grad_g, float* grad_b,
+                                    const float* __restrict__ extra_row, float extra_scale) {
+  wgrad_finish_row(blockIdx.x, partial, P, rows_partial, ld_partial, bias_partial, K, row0, kmap, in_scale, v, g, grad_w, grad_g, grad_b,
+                   extra_row, extra_scale);
+}
+// many layers in one launch: blockIdx.y selects the job (jobs must not share destination rows)
+struct FinishJob {
+  const float* partial; const float* bias_partial; const int* kmap; const float* v; const float* g;
+  float* grad_w; float* grad_g; float* grad_b; const float* extra_row;
+  int P, rows_partial, ld_partial, K, row0, nrows;
+  float in_scale, extra_scale;
+};
+__global__ void wgrad_finish_batch_kernel(const FinishJob* __restrict__ jobs) {
+  const FinishJob j = jobs[blockIdx.y];
+  if (int(blockIdx.x) >= j.nrows) return;
+  wgrad_finish_row(blockIdx.x, j.partial, j.P, j.rows_partial, j.ld_partial, j.bias_partial, j.K, j.row0, j.kmap, j.in_scale, j.v, j.g,
+                   j.grad_w, j.grad_g, j.grad_b, j.extra_row, j.extra_scale);
+}
+int wgrad_finish_batch(const void* jobs_dev, int n_jobs, int max_rows, int max_k, cudaStream_t stream) {
+  if (n_jobs <= 0 || max_rows <= 0) return NERO_OK;
+  if (!jobs_dev || max_k <= 0 || max_k > 1024) return NERO_ERR_ARG;
+  wgrad_finish_batch_kernel<<<dim3(max_rows, n_jobs), dim3(256, 4), 4 * max_k * sizeof(float), stream>>>(static_cast<const FinishJob*>(jobs_dev));
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
 }
 
 int wgrad_finish(const float* partial, int P, int rows_partial, int ld_partial, const float* bias_partial, int K,

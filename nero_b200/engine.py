@@ -499,6 +499,7 @@ class ShapeEngine:
         self.lut = c.FG_LUT
         self.grads = Grads(list(params.parameters()))
         self.ws = ops.WgradWorkspace(dev)
+        self.ws.defer = True      # weight-gradient reductions are queued and run as one batched launch per backward pass
         self.w = None
         self.cap = (0, 0)
         n, nb = cfg['n_samples'], cfg['n_bg_samples']
@@ -585,6 +586,7 @@ class ShapeEngine:
         w['REG_DSDF'][:k, 0].copy_(d_sdf_vals)
         cap = self.cap[0] * self.cap[1]
         self.sdf.value_backward(self.ws, w['REG_X0'], w['REG_H'], w['REG_DSDF'], w['ABAR'], w['dHa'], w['REG_N'], cap)
+        self.ws.flush()
 
     def _alloc_backward(self):
         if self.bw_ready:
@@ -875,3 +877,4 @@ class ShapeEngine:
             var_p.grad.add_((w['D_INV_S'][0] * 10.0 * inv_s * inr).reshape(var_p.shape))
         # ---- SDF network (value + gradient paths)
         self.sdf.backward(ws, w, n_in, cap, None)
+        ws.flush()

@@ -197,6 +197,7 @@ class MaterialEngine:
         self.mcap = M
         if self.ws is None:
             self.ws = ops.WgradWorkspace(self.dev)
+            self.ws.defer = True
 
     def materials_forward(self, pts):
         """predict_materials before the roughness rescale: sigmoid outputs (metallic [M,1], roughness [M,1], albedo [M,3])."""
@@ -228,6 +229,7 @@ class MaterialEngine:
         self.m_met.backward(self.ws, Mat(dm, O_MET), y, w['ACT']['met'], *a, None, M, dX=dy, dx_ncol=256, dx_addend=dy, dHc=w['dHc'])
         self.m_alb.backward(self.ws, Mat(dm, O_ALB), y, w['ACT']['alb'], *a, None, M, dX=dy, dx_ncol=256, dx_addend=dy, dHc=w['dHc'])
         self.feats.backward(self.ws, w, M)
+        self.ws.flush()
 
     # ------------------------------------------------------------------ Monte-Carlo lights
     def _alloc_lights(self, P):
@@ -248,6 +250,7 @@ class MaterialEngine:
         self.w, self.cap, self.ldeo = w, P, ldeo
         if self.ws is None:
             self.ws = ops.WgradWorkspace(dev)
+            self.ws.defer = True
 
     def _params(self, st):
         w = self.w
@@ -324,6 +327,7 @@ class MaterialEngine:
         if n_hit > 0:
             self.m_inner.backward(self.ws, Mat(w['DPRE_I']), Mat(w['EI']), [a[n_miss:] for a in A], D[0][n_miss:], D[1][n_miss:], None, n_hit,
                                   dX=Mat(w['dEI'], 52), dx_ncol=72, dHc=D[2][n_miss:])
+        self.ws.flush()
         ops.mc('nero_mc_dir_bwd', q)
         return w['dA'][:st['P']] + w['dA2'][:st['P']]
 

@@ -228,11 +228,73 @@ def _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, osc
         tail.t[:M, tail.c0:tail.c0 + ncol_out - ncol_main] = oscale * acc[:, ncol_main:]
 
 
+_FINISH_JOB = None
+
+
+def _finish_job_dtype():
+    global _FINISH_JOB
+    if _FINISH_JOB is None:
+        import numpy as np
+        _FINISH_JOB = np.dtype([('partial', 'u8'), ('bias_partial', 'u8'), ('kmap', 'u8'), ('v', 'u8'), ('g', 'u8'), ('grad_w', 'u8'),
+                                ('grad_g', 'u8'), ('grad_b', 'u8'), ('extra_row', 'u8'), ('P', 'i4'), ('rows_partial', 'i4'),
+                                ('ld_partial', 'i4'), ('K', 'i4'), ('row0', 'i4'), ('nrows', 'i4'), ('in_scale', 'f4'),
+                                ('extra_scale', 'f4')])
+        assert _FINISH_JOB.itemsize == 104
+    return _FINISH_JOB
+
+
 class WgradWorkspace:
-    def __init__(self, device, P=74, rows=256, ld=384):
+    """Split-K partial buffers of the weight-gradient GEMMs.  With `defer` set (the engines do), every nero_wgrad launch
+    gets its own partial slot and its reduction / weight-norm chain rule is queued; `flush()` runs all queued reductions
+    in ONE nero_wgrad_finish_batch launch.  Jobs that would accumulate into the same gradient rows are never queued
+    together (the queue is flushed first), so the batched kernel has no write conflicts."""
+
+    def __init__(self, device, P=74, rows=256, ld=384, max_slots=48):
         self.P, self.rows, self.ld = P, rows, ld
-        self.partial = torch.zeros(P, rows, ld, dtype=torch.float32, device=device)
-        self.bias_partial = torch.zeros(P, rows, dtype=torch.float32, device=device)
+        self.device, self.max_slots = device, max_slots
+        self.slots = []
+        self.jobs, self.dest, self.keep = [], set(), []
+        self.defer = False
+        self._tab = None
+        self._slot()
+
+    def _slot(self):
+        i = len(self.jobs)
+        while len(self.slots) <= i:
+            self.slots.append((torch.zeros(self.P, self.rows, self.ld, dtype=torch.float32, device=self.device),
+                               torch.zeros(self.P, self.rows, dtype=torch.float32, device=self.device)))
+        return self.slots[i]
+
+    @property
+    def partial(self):
+        return self._slot()[0]
+
+    @property
+    def bias_partial(self):
+        return self._slot()[1]
+
+    def enqueue(self, job, dest_key, keep):
+        self.jobs.append(job)
+        self.dest.add(dest_key)
+        self.keep.append(keep)
+        if len(self.jobs) >= self.max_slots:
+            self.flush()
+
+    def flush(self):
+        global launch_count
+        if not self.jobs:
+            return
+        import numpy as np
+        arr = np.zeros(len(self.jobs), dtype=_finish_job_dtype())
+        for i, j in enumerate(self.jobs):
+            arr[i] = j
+        max_rows = int(arr['nrows'].max())
+        max_k = int(arr['K'].max())
+        self._tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.device, non_blocking=True)
+        rc = lib.nero_wgrad_finish_batch(_ptr(self._tab), len(self.jobs), max_rows, max_k, _stream())
+        _check(rc, 'nero_wgrad_finish_batch')
+        launch_count += 1
+        self.jobs, self.dest, self.keep = [], set(), []
 
 
 def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: PreparedLayer, grad_w, grad_g, grad_b,
@@ -245,6 +307,9 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
     n_rows_pad = ceil_div(n_valid, 16) * 16
     k_pad = ceil_div(layer.k_layout, 64) * 64
     assert k_pad <= ws.ld and n_rows_pad <= ws.rows
+    if ws.defer and grad_w is not None and (grad_w.data_ptr(), layer.row0) in ws.dest:
+        ws.flush()                      # a queued job already accumulates into these rows
+    partial_t, bias_t = ws.partial, ws.bias_partial
     if DEBUG_GEMM == 'torch':
         M = _m_of(m_ptr, m_cap)
         dw = dY.t[:M, dY.c0:dY.c0 + n_valid].t() @ X.t[:M, X.c0:X.c0 + layer.k_layout]
@@ -258,7 +323,7 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
         P = ws.P
         rc = 0 if DRY_RUN else lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
                             dY2.ptr() if dY2 else None, dY2.ld if dY2 else 0, X2.ptr() if X2 else None, X2.ld if X2 else 0,
-                            _ptr(ws.partial), ws.ld, ws.rows, _ptr(ws.bias_partial), n_rows_pad, k_pad, P, _ptr(m_ptr),
+                            _ptr(partial_t), ws.ld, ws.rows, _ptr(bias_t), n_rows_pad, k_pad, P, _ptr(m_ptr),
                             m_cap, _stream())
         _check(rc, 'nero_wgrad')
         launch_count += ceil_div(n_rows_pad, 128) * max(1, ceil_div(k_pad, 256))
@@ -267,9 +332,16 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
         assert grad_w is not None and (grad_b is not None or not with_bias) and (g is None or grad_g is not None)
         assert dY.c0 + n_valid <= dY.t.shape[1] and X.c0 + k_valid <= X.t.shape[1], (dY.c0, n_valid, dY.t.shape, X.c0, k_valid, X.t.shape)
         return
-    rc = lib.nero_wgrad_finish(_ptr(ws.partial), ws.P, ws.rows, ws.ld, _ptr(ws.bias_partial) if with_bias else None,
+    w_ = layer.weight.detach()
+    if ws.defer and DEBUG_GEMM != 'torch':
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        job = (ptr(partial_t), ptr(bias_t) if with_bias else 0, ptr(layer.kmap), ptr(w_), ptr(g), ptr(grad_w), ptr(grad_g),
+               ptr(grad_b) if with_bias else 0, 0, ws.P, ws.rows, ws.ld, layer.K, layer.row0, layer.nrows, 1.0, 0.0)
+        ws.enqueue(job, (grad_w.data_ptr(), layer.row0), (w_, g))
+        return
+    rc = lib.nero_wgrad_finish(_ptr(partial_t), ws.P, ws.rows, ws.ld, _ptr(bias_t) if with_bias else None,
                                layer.K, layer.row0, layer.nrows, _ptr(layer.kmap), ctypes.c_float(1.0),
-                               _ptr(layer.weight.detach()), _ptr(g), _ptr(grad_w), _ptr(grad_g),
+                               _ptr(w_), _ptr(g), _ptr(grad_w), _ptr(grad_g),
                                _ptr(grad_b) if with_bias else None, None, ctypes.c_float(0.0), _stream())
     _check(rc, 'nero_wgrad_finish')
     launch_count += 1
