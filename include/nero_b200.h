@@ -216,6 +216,11 @@ int nero_mc_dir_bwd(const nero_mc_params* q, void* stream);
 /* MaterialFeatsNetwork inputs (field.py:660-689): PE8 rows, skip-concat tail, xyz for the predictor input */
 int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, void* stream);
 
+/* nero_prep_weight for many layers in ONE launch.  jobs_dev: device array of n_jobs records
+ *   { const float* v, *g; const int* kmap; void* img_f, *img_t; float* w_eff;
+ *     int K, row0, nrows, rows_pad_f, rows_pad_t, t_c0, t_ncols, ld_weff; float in_scale; int pad; }   (88 bytes each) */
+int nero_prep_weight_batch(const void* jobs_dev, int n_jobs, int max_rows, void* stream);
+
 /* nero_wgrad_finish for many layers in ONE launch.  jobs_dev: device array of n_jobs records
  *   { const float* partial, *bias_partial; const int* kmap; const float* v, *g; float* grad_w, *grad_g, *grad_b;
  *     const float* extra_row; int P, rows_partial, ld_partial, K, row0, nrows; float in_scale, extra_scale; }

@@ -34,6 +34,7 @@ int wgrad_finish(const float* partial, int P, int rows_partial, int ld_partial, 
                  float* grad_g, float* grad_b, const float* extra_row, float extra_scale, cudaStream_t stream);
 int colsum(const float* X, int ldx, int ncol, const float* w, int ldw, const int* m_ptr, int m_cap, float* out, cudaStream_t stream);
 int wgrad_finish_batch(const void* jobs_dev, int n_jobs, int max_rows, int max_k, cudaStream_t stream);
+int prep_weight_batch(const void* jobs_dev, int n_jobs, int max_rows, cudaStream_t stream);
 int adam_flat(float* p, const float* g, float* m, float* v, long n, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2,
               float wd, cudaStream_t st);
 }  // namespace nero
@@ -215,6 +216,9 @@ int nero_mc_fill(const nero_mc_params* q, void* stream) { return q ? mc_fill(*q,
 int nero_mc_combine_fwd(const nero_mc_params* q, void* stream) { return q ? mc_combine_fwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
 int nero_mc_combine_bwd(const nero_mc_params* q, void* stream) { return q ? mc_combine_bwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
 int nero_mc_dir_bwd(const nero_mc_params* q, void* stream) { return q ? mc_dir_bwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_prep_weight_batch(const void* jobs_dev, int n_jobs, int max_rows, void* stream) {
+  return prep_weight_batch(jobs_dev, n_jobs, max_rows, (cudaStream_t)stream);
+}
 int nero_wgrad_finish_batch(const void* jobs_dev, int n_jobs, int max_rows, int max_k, void* stream) {
   return wgrad_finish_batch(jobs_dev, n_jobs, max_rows, max_k, (cudaStream_t)stream);
 }

@@ -37,11 +37,10 @@ __device__ __forceinline__ void img_store(uint8_t* img, int rows_pad, int r, int
   *reinterpret_cast<__nv_bfloat16*>(base + size_t(rows_pad) * 128 + off) = lo;
 }
 
-__global__ void prep_weight_kernel(const float* __restrict__ v, const float* __restrict__ g, int K, int row0,
+__device__ __forceinline__ void prep_weight_row(int r, const float* __restrict__ v, const float* __restrict__ g, int K, int row0,
                                    const int* __restrict__ kmap, float in_scale, uint8_t* img_f, int rows_pad_f,
                                    uint8_t* img_t, int rows_pad_t, int t_c0, int t_ncols, float* w_eff, int ld_weff) {
   __shared__ float sh[32];
-  const int r = blockIdx.x;       // local row
   const int n = row0 + r;         // layer row
   const float* vr = v + size_t(n) * K;
   float scale = 1.0f;
@@ -59,6 +58,31 @@ __global__ void prep_weight_kernel(const float* __restrict__ v, const float* __r
     if (img_f) img_store(img_f, rows_pad_f, r, kc, ws);
     if (img_t && kc >= t_c0 && kc < t_c0 + t_ncols) img_store(img_t, rows_pad_t, kc - t_c0, r, ws);
   }
+}
+
+__global__ void prep_weight_kernel(const float* __restrict__ v, const float* __restrict__ g, int K, int row0,
+                                   const int* __restrict__ kmap, float in_scale, uint8_t* img_f, int rows_pad_f,
+                                   uint8_t* img_t, int rows_pad_t, int t_c0, int t_ncols, float* w_eff, int ld_weff) {
+  prep_weight_row(blockIdx.x, v, g, K, row0, kmap, in_scale, img_f, rows_pad_f, img_t, rows_pad_t, t_c0, t_ncols, w_eff, ld_weff);
+}
+// all layers of a network in one launch: blockIdx.y selects the job
+struct PrepJob {
+  const float* v; const float* g; const int* kmap; uint8_t* img_f; uint8_t* img_t; float* w_eff;
+  int K, row0, nrows, rows_pad_f, rows_pad_t, t_c0, t_ncols, ld_weff;
+  float in_scale; int pad_;
+};
+__global__ void prep_weight_batch_kernel(const PrepJob* __restrict__ jobs) {
+  const PrepJob j = jobs[blockIdx.y];
+  if (int(blockIdx.x) >= j.nrows) return;
+  prep_weight_row(blockIdx.x, j.v, j.g, j.K, j.row0, j.kmap, j.in_scale, j.img_f, j.rows_pad_f, j.img_t, j.rows_pad_t, j.t_c0, j.t_ncols,
+                  j.w_eff, j.ld_weff);
+}
+int prep_weight_batch(const void* jobs_dev, int n_jobs, int max_rows, cudaStream_t stream) {
+  if (n_jobs <= 0 || max_rows <= 0) return NERO_OK;
+  if (!jobs_dev) return NERO_ERR_ARG;
+  prep_weight_batch_kernel<<<dim3(max_rows, n_jobs), 128, 0, stream>>>(static_cast<const PrepJob*>(jobs_dev));
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
 }
 
 int prep_weight(const float* v, const float* g, int K, int row0, int nrows, const int* kmap, float in_scale,

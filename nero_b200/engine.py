@@ -519,10 +519,13 @@ class ShapeEngine:
         return ps + ([self.m_human] if self.human else [])
 
     def prepare_weights(self):
-        self.sdf.prep()
-        self.nerf.prep()
-        for m in self.predictors():
-            m.prep()
+        """Fold weight-norm and rebuild the tensor-core operand images of every layer (one batched launch)."""
+        if getattr(self, '_all_layers', None) is None:
+            ls = self.sdf.L + [self.sdf.L8f, self.sdf.L8s] + self.nerf.all_layers()
+            for m in self.predictors():
+                ls += m.layers
+            self._all_layers = ls
+        ops.prep_batch(self._all_layers)
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, R, S):

@@ -170,9 +170,12 @@ class MaterialEngine:
         return [m for m in (self.m_met, self.m_rough, self.m_alb, self.m_outer, self.m_inner, self.m_human) if m is not None]
 
     def prepare_weights(self):
-        self.feats.prep()
-        for m in self.predictors():
-            m.prep()
+        if getattr(self, '_all_layers', None) is None:
+            ls = self.feats.L0 + self.feats.L1
+            for m in self.predictors():
+                ls += m.layers
+            self._all_layers = ls
+        ops.prep_batch(self._all_layers)
 
     # ------------------------------------------------------------------ tracing (renderer.py:719-729)
     def trace(self, rays_o, rays_d):
