@@ -216,6 +216,10 @@ int nero_mc_dir_bwd(const nero_mc_params* q, void* stream);
 /* MaterialFeatsNetwork inputs (field.py:660-689): PE8 rows, skip-concat tail, xyz for the predictor input */
 int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, void* stream);
 
+/* sizeof() of the structures that cross this ABI, for bindings to verify their mirror layouts:
+ * 0 nero_chain_layer, 1 nero_chain_params, 2 nero_mc_params, 3 finish job record, 4 prep job record. */
+int nero_abi_sizeof(int which);
+
 /* nero_prep_weight for many layers in ONE launch.  jobs_dev: device array of n_jobs records
  *   { const float* v, *g; const int* kmap; void* img_f, *img_t; float* w_eff;
  *     int K, row0, nrows, rows_pad_f, rows_pad_t, t_c0, t_ncols, ld_weff; float in_scale; int pad; }   (88 bytes each) */

@@ -216,6 +216,16 @@ int nero_mc_fill(const nero_mc_params* q, void* stream) { return q ? mc_fill(*q,
 int nero_mc_combine_fwd(const nero_mc_params* q, void* stream) { return q ? mc_combine_fwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
 int nero_mc_combine_bwd(const nero_mc_params* q, void* stream) { return q ? mc_combine_bwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
 int nero_mc_dir_bwd(const nero_mc_params* q, void* stream) { return q ? mc_dir_bwd(*q, (cudaStream_t)stream) : NERO_ERR_ARG; }
+int nero_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return int(sizeof(nero_chain_layer));
+    case 1: return int(sizeof(nero_chain_params));
+    case 2: return int(sizeof(nero_mc_params));
+    case 3: return 104;   /* finish job record (k_weights.cu FinishJob) */
+    case 4: return 88;    /* prep job record (k_weights.cu PrepJob) */
+    default: return -1;
+  }
+}
 int nero_prep_weight_batch(const void* jobs_dev, int n_jobs, int max_rows, void* stream) {
   return prep_weight_batch(jobs_dev, n_jobs, max_rows, (cudaStream_t)stream);
 }

@@ -71,6 +71,7 @@ struct PrepJob {
   int K, row0, nrows, rows_pad_f, rows_pad_t, t_c0, t_ncols, ld_weff;
   float in_scale; int pad_;
 };
+static_assert(sizeof(PrepJob) == 88, "PrepJob layout is part of the C ABI (nero_prep_weight_batch)");
 __global__ void prep_weight_batch_kernel(const PrepJob* __restrict__ jobs) {
   const PrepJob j = jobs[blockIdx.y];
   if (int(blockIdx.x) >= j.nrows) return;
@@ -164,6 +165,7 @@ struct FinishJob {
   int P, rows_partial, ld_partial, K, row0, nrows;
   float in_scale, extra_scale;
 };
+static_assert(sizeof(FinishJob) == 104, "FinishJob layout is part of the C ABI (nero_wgrad_finish_batch)");
 __global__ void wgrad_finish_batch_kernel(const FinishJob* __restrict__ jobs) {
   const FinishJob j = jobs[blockIdx.y];
   if (int(blockIdx.x) >= j.nrows) return;

@@ -41,3 +41,15 @@ def test_sass_uses_blackwell_tensor_path():
     for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
         assert mnemonic in out, mnemonic
     assert 'HMMA.' not in out.replace('UTCHMMA', ''), 'legacy mma.sync path must not be used'
+
+
+def test_binding_struct_layouts_match_the_library():
+    """ctypes / numpy mirrors of the structures that cross the C ABI have the sizes the library was compiled with."""
+    import numpy as np
+    from nero_b200 import ops
+    lib = ops.lib
+    assert lib.nero_abi_sizeof(0) == ctypes.sizeof(ops._ChainLayer)
+    assert lib.nero_abi_sizeof(1) == ctypes.sizeof(ops._ChainParams)
+    assert lib.nero_abi_sizeof(2) == ctypes.sizeof(ops.McParams)
+    assert lib.nero_abi_sizeof(3) == ops._finish_job_dtype().itemsize
+    assert lib.nero_abi_sizeof(4) == 88 and lib.nero_abi_sizeof(99) == -1

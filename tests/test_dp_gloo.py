@@ -70,3 +70,61 @@ def test_ray_sharded_dp_matches_single_process():
 def test_shard_slices_cover_batch():
     idx = np.concatenate([np.arange(64)[dp.shard_slice(64, r, 4)] for r in range(4)])
     assert (idx == np.arange(64)).all()
+
+
+# ------------------------------------------------------------------------------------------------ stage II (surface points)
+MCFG = {'shader_cfg': {'human_lights': True, 'diffuse_sample_num': 8, 'specular_sample_num': 8}}
+MSTEP = 5000      # >= 2000: every stage-II loss term is a plain mean over points (field.py:1079: the min/max regulariser of
+                  # earlier steps is a SUM over the batch and would need a factor `world` per rank)
+
+
+def _material_grads(sd, batch, rands, sl, verts, tris):
+    import nero_oracle_mat as OM
+    p = {k: v.clone().requires_grad_(torch.is_floating_point(v) and not k.endswith('light_pts')) for k, v in sd.items()}
+    tabs = (OM.direction_samples(8), OM.direction_samples(8))
+    b = {k: v[sl] for k, v in batch.items()}
+    r = {k: v[sl] for k, v in rands.items()}
+    out = OM.material_train_outputs(p, MCFG, tabs, lambda o, d: OM.renderer_trace(verts, tris, o, d), b, MSTEP, r)
+    OM.material_training_loss(out).backward()
+    names = sorted(k for k in p if p[k].grad is not None)
+    return torch.cat([p[k].grad.reshape(-1) for k in names])
+
+
+def _material_setup():
+    import nero_oracle_mat as OM
+    from helpers import build_material_params
+    verts, tris = OM.test_scene(1)
+    sd = build_material_params(MCFG['shader_cfg'])
+    batch = OM.synthetic_surface_batch(verts, tris, 8, seed=5)
+    return sd, batch, OM.draw_rands(8), verts, tris
+
+
+def _material_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    sd, batch, rands, verts, tris = _material_setup()
+    flat = _material_grads(sd, batch, rands, dp.shard_slice(8, rank, world), verts, tris)
+    dp.sync_gradients(flat, world)
+    if rank == 0:
+        q.put(flat.numpy())
+    dist.destroy_process_group()
+
+
+def test_point_sharded_material_dp_matches_single_process():
+    """Stage II shards over surface points: equal shards + mean losses => averaged shard gradients == full-batch gradient."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_material_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    got = q.get(timeout=300)
+    for p_ in procs:
+        p_.join(timeout=60)
+    sd, batch, rands, verts, tris = _material_setup()
+    want = _material_grads(sd, batch, rands, slice(0, 8), verts, tris).numpy()
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max() + 1e-9
