@@ -124,9 +124,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     import nero_oracle as O
-    cfg = {}
+    bear = args.workload == 'bear'        # BASELINE.json configs[2] / SURVEY 8d config 3: human light on, 2048 rays on one GPU
+    cfg = {'shader_config': {'human_light': True}} if bear else {}
     net, sd = build_net(cfg, dev)
-    R = RAYS_PER_GPU                      # weak scaling: 1024 rays per GPU, global batch = 1024 * world
+    R = 2048 if bear else RAYS_PER_GPU    # weak scaling: fixed rays per GPU, global batch = R * world
     rays = O.synthetic_rays(R * world, seed=6033)
     r = {k: v[rank * R:(rank + 1) * R].to(dev).contiguous() for k, v in rays.items()}
     from nero_b200.optim import FlatAdam
@@ -210,12 +211,12 @@ def run_ours(args):
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank == 0:
         peak_tf, peak_bw, which = measured_peaks()
-        F = algorithmic_flops(R, n_in, n_out, p_occ)
+        F = algorithmic_flops(R, n_in, n_out, p_occ, human=bear)
         line = {
             'metric': 'train rays/sec (128 samples/ray)', 'value': R * world / (ms * 1e-3), 'unit': 'rays/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32 (split-bf16 x3 tensor-core MMAs, fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'rays_per_gpu': R, 'global_rays': R * world, 'n_in': n_in, 'n_out': n_out, 'p_occ': p_occ,
+            'config': {'workload': WORKLOAD.replace('bell', 'bear_human_light').replace('1024rays', '2048rays') if bear else WORKLOAD, 'rays_per_gpu': R, 'global_rays': R * world, 'n_in': n_in, 'n_out': n_out, 'p_occ': p_occ,
                        'parallelism': f'ray-sharded dp{world}, one NCCL all-reduce of the flat grad buffer' if world > 1 else 'single gpu',
                        'l2': 'per-step working set ~6 GB of activations >> 126 MB L2 (inputs larger than L2)',
                        'optimizer': 'Adam (nero_adam_flat over the flat parameter buffer) inside the timed region'},
@@ -358,6 +359,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
+    ap.add_argument('--workload', default='bell', choices=['bell', 'bear'],
+                    help="bell = BASELINE.json configs[1] (the headline, default); bear = configs[2]: human light, 2048 rays")
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
