@@ -2,6 +2,7 @@
 // so the hand-derived backward formulas are checked against the oracle's autograd without a GPU.
 // Built by tests/test_hostcheck_math.py with nvcc; never part of libnero_b200.so.
 #include "../../nero_b200/csrc/math_shade.cuh"
+#include "../../nero_b200/csrc/math_mc.cuh"
 using namespace nero;
 
 static IdeTable g_tab;
@@ -83,4 +84,20 @@ void hc_human(int n, const float* p, const float* r, const float* pose, const fl
   }
 }
 void hc_srgb(int n, const float* x, float* y, float* dy) { for (int i = 0; i < n; ++i) { y[i] = linear_to_srgb(x[i]); dy[i] = dlinear_to_srgb(x[i]); } }
+// stage II: sampled direction, specular weight and Schlick factor of one (point, sample) with forward-mode d/d(roughness)
+void hc_mc(int n, const float* normal, const float* view, const float* a, const float* az01, const float* el, const int* spec, int ggx,
+           float frac_d, float frac_s, float* dir, float* w, float* f5, float* ddir, float* dw, float* df5) {
+  for (int i = 0; i < n; ++i) {
+    const McPoint q = mc_point(normal + 3 * i, view + 3 * i);
+    const Dual A = mk(a[i], 1.f);
+    Dual d[3];
+    const float ang = mc_azimuth(az01[i], 0.f, false);
+    if (spec[i]) mc_specular_dir<Dual>(q, ang, el[i], A, d);
+    else { float df[3]; mc_diffuse_dir(q, ang, el[i], df); for (int k = 0; k < 3; ++k) d[k] = mk(df[k]); }
+    Dual W, F;
+    mc_weights<Dual>(q, d, A, spec[i] != 0, frac_d, frac_s, ggx, W, F);
+    for (int k = 0; k < 3; ++k) { dir[3 * i + k] = d[k].v; ddir[3 * i + k] = d[k].d; }
+    w[i] = W.v; dw[i] = W.d; f5[i] = F.v; df5[i] = F.d;
+  }
+}
 }

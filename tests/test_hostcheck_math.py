@@ -17,7 +17,7 @@ SO = os.path.join(HERE, 'hostcheck', 'libhostcheck.so')
 
 @pytest.fixture(scope='module')
 def hc():
-    deps = [SRC] + [os.path.join(HERE, '..', 'nero_b200', 'csrc', f) for f in ('math_enc.cuh', 'math_shade.cuh', 'common.cuh')]
+    deps = [SRC] + [os.path.join(HERE, '..', 'nero_b200', 'csrc', f) for f in ('math_enc.cuh', 'math_shade.cuh', 'math_mc.cuh', 'common.cuh')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['/usr/local/cuda/bin/nvcc', '-O2', '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '--fmad=false',
                                '-Wno-deprecated-gpu-targets', '-o', SO, SRC])
@@ -197,3 +197,50 @@ def test_human(hc):
     close(oe, enc, 1e-3, 1e-4, 'ipe')
     close(odr, rd.grad, 5e-3, 5e-3, 'human dr')
     close(odg, rg.grad[:, 0], 5e-3, 5e-3, 'human drough')
+
+
+@pytest.mark.parametrize('ggx', [0, 1])
+def test_mc_sampling_and_brdf_weights(hc, ggx):
+    """math_mc.cuh (stage II): sampled directions, D*G/(4 NoV p) and (1-HoV)^5 vs the oracle's shade_mixed terms, and their
+    forward-mode d/d(roughness) vs the oracle's autograd in float64 (network/field.py:768-812, 932-975)."""
+    import nero_oracle_mat as OM
+    g = torch.Generator().manual_seed(9)
+    n = 600
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    view = torch.nn.functional.normalize(nrm + 0.8 * torch.randn(n, 3, generator=g), dim=-1)
+    a = 0.05 + 0.9 * torch.rand(n, 1, generator=g)
+    az = torch.rand(n, generator=g)
+    el = 0.06 + 0.94 * torch.rand(n, generator=g)
+    spec = (torch.arange(n) % 3 != 0)
+    fd, fs = 2.0 / 3.0, 1.0 / 3.0
+    scfg = OM.shader_cfg({'geometry_type': 'ggx_smith' if ggx else 'schlick'})
+    # oracle, one sample per point, float64, roughness requires grad
+    N, V = nrm.double(), view.double()
+    A = a.double().requires_grad_(True)
+    refl = torch.sum(V * N, -1, keepdim=True) * N * 2 - V
+    tab = torch.stack([az, el], -1).double()
+    dd = torch.stack([OM.sample_diffuse_directions(tab[i:i + 1], N[i:i + 1])[0, 0] for i in range(n)])
+    ds = torch.stack([OM.sample_specular_directions(tab[i:i + 1], refl[i:i + 1], A[i:i + 1])[0, 0] for i in range(n)])
+    d = torch.where(spec[:, None], ds, dd)
+    H = torch.nn.functional.normalize(V + d, dim=-1)
+    HoV = OM.saturate_dot(H, V)
+    NoH, NoL, NoV = OM.saturate_dot(N, H), OM.saturate_dot(N, d), OM.saturate_dot(N, V)
+    D = OM.distribution_ggx(NoH, A)
+    prob = torch.where(spec[:, None], D * NoH / (4 * HoV + 1e-5) * fs, NoL / np.pi * fd)
+    w = D * OM.geometry_term(scfg, NoV, NoL, A) / (4 * NoV * prob + 1e-5)
+    f5 = torch.clamp(1.0 - HoV, min=0.0, max=1.0) ** 5.0
+    gw = torch.autograd.grad(w.sum(), A, retain_graph=True)[0][:, 0]
+    gf = torch.autograd.grad(f5.sum(), A, retain_graph=True)[0][:, 0]
+    gd = torch.stack([torch.autograd.grad(d[:, k].sum(), A, retain_graph=True)[0][:, 0] for k in range(3)], -1)
+    o = {k: np.zeros(s_, np.float32) for k, s_ in dict(dir=(n, 3), w=n, f5=n, ddir=(n, 3), dw=n, df5=n).items()}
+    hc.hc_mc(n, P(f32(nrm)), P(f32(view)), P(f32(a[:, 0])), P(f32(az)), P(f32(el)), P(np.ascontiguousarray(spec.numpy(), np.int32)), ggx,
+             ctypes.c_float(fd), ctypes.c_float(fs), P(o['dir']), P(o['w']), P(o['f5']), P(o['ddir']), P(o['dw']), P(o['df5']))
+    close(o['dir'], d, 1e-5, 2e-6, 'direction')
+    close(o['ddir'], gd, 2e-4, 2e-5, 'd direction / d roughness')
+    ok = (NoV[:, 0] > 0.05) & (w[:, 0].abs() < 1e4)           # away from the 1e-5-regularised singular corners
+    wn, gwn = w[:, 0].detach().numpy(), gw.numpy()
+    m = ok.numpy()
+    close(o['w'][m], wn[m], 2e-4, 1e-5, 'specular weight')
+    close(o['dw'][m], gwn[m], 2e-3, 2e-3 * np.abs(gwn[m]).mean(), 'd weight / d roughness')
+    close(o['f5'], f5[:, 0], 2e-4, 1e-6, 'schlick factor')
+    close(o['df5'], gf, 2e-3, 1e-5, 'd schlick / d roughness')
