@@ -240,6 +240,25 @@ class NeROShapeRenderer(nn.Module):
         outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], batch['rgbs'])
         return outputs
 
+    def nvs(self, pose, K, h, w):
+        """Novel-view colour image for a numpy pose [3,4] / intrinsics [3,3] (network/renderer.py:189-222): 1024-ray chunks,
+        no jitter, step 300000.  Only `ray_rgb` is returned, so the validation extras of is_train=False are not computed."""
+        dev = self.deviation_network.variance.device
+        Kt = torch.from_numpy(np.asarray(K, np.float32)).unsqueeze(0).to(dev)
+        poses = torch.from_numpy(np.asarray(pose, np.float32)).unsqueeze(0).to(dev)
+        ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
+        coords = torch.stack([xs, ys], -1).float().reshape(1, h * w, 2)
+        coords = torch.cat([coords + 0.5, torch.ones(1, h * w, 1, device=dev)], 2)
+        dirs = (coords @ torch.inverse(Kt).permute(0, 2, 1)).reshape(h * w, 3)
+        idxs = torch.zeros(h * w, 1, dtype=torch.int64, device=dev)
+        out = []
+        with torch.no_grad():
+            for ri in range(0, h * w, 1024):
+                cur = {'dirs': dirs[ri:ri + 1024], 'idxs': idxs[ri:ri + 1024]}
+                rays_o, rays_d, near, far, hp = self._process_ray_batch(cur, poses)
+                out.append(self.render(rays_o, rays_d, near, far, hp, 0, 0, is_train=True, step=300000)['ray_rgb'].cpu().numpy())
+        return np.reshape(np.concatenate(out, 0), [h, w, 3])
+
     def test_step(self, index, step):
         """Full-image validation render in chunks of `test_ray_num` rays (network/renderer.py:274-316).  Needs the host
         repo's `dataset` package (database access) exactly like the reference; the per-chunk render runs on the CUDA path."""
