@@ -244,7 +244,7 @@ def run_ours(args):
                                                        'frac': prof['flops'] / prof['seconds'] / 1e12 / peak_tf},
                                 'note': 'achieved counts ALGORITHMIC fp32 GEMM flops (2*M*K*N of the un-padded layers); the '
                                         'split-bf16 scheme issues 3 bf16 MMAs per product, so 1/3 of peak is its ceiling'}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # the CPU leg runs on rank 0 at N=1 only
             line['cpu_baseline'] = cpu_baseline(rays_n=128, steps=1)
         print(json.dumps(line))
     if world > 1:
