@@ -74,10 +74,9 @@ class ClockSampler(threading.Thread):
 
 
 def build_net(cfg, device):
-    import nero_oracle as O
-    from nero_b200 import params as P
+    from nero_b200 import params as P, synthetic
     from nero_b200.renderer import NeROShapeRenderer
-    sd = O.perturb_params(P.build_shape_state_dict(cfg, seed=6033))
+    sd = synthetic.perturb_params(P.build_shape_state_dict(cfg, seed=6033))
     net = NeROShapeRenderer(cfg, training=False)
     net.load_state_dict(sd)
     return net.to(device), sd
@@ -123,12 +122,12 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    import nero_oracle as O
+    from nero_b200 import synthetic
     bear = args.workload == 'bear'        # BASELINE.json configs[2] / SURVEY 8d config 3: human light on, 2048 rays on one GPU
     cfg = {'shader_config': {'human_light': True}} if bear else {}
     net, sd = build_net(cfg, dev)
     R = 2048 if bear else RAYS_PER_GPU    # weak scaling: fixed rays per GPU, global batch = R * world
-    rays = O.synthetic_rays(R * world, seed=6033)
+    rays = synthetic.synthetic_rays(R * world, seed=6033)
     r = {k: v[rank * R:(rank + 1) * R].to(dev).contiguous() for k, v in rays.items()}
     from nero_b200.optim import FlatAdam
     opt = FlatAdam(net, lr=5e-4 * 0.05)        # one nero_adam_flat launch over the flat parameter / gradient buffers

@@ -35,13 +35,13 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-points', type=int, default=16)
     args = ap.parse_args()
-    import nero_oracle as O
-    import nero_oracle_mat as OM
+    from nero_b200 import synthetic as O
+    from nero_b200 import synthetic as SY
     from nero_b200 import ops, params as PR
     from nero_b200.material import NeROMaterialRenderer
     assert not ops.DEBUG_GEMM and not ops.DRY_RUN
     dev = torch.device('cuda', 0)
-    verts, tris = OM.test_scene(5)
+    verts, tris = SY.test_scene(5)
     t0 = time.time()
     net = NeROMaterialRenderer(CFG, is_train=False, mesh=(verts, tris))
     sd = O.perturb_params(PR.build_material_state_dict(CFG['shader_cfg'], seed=6033))
@@ -129,6 +129,7 @@ def main():
             'phases': phases, 'trace': {'ms': trace_ms, 'rays_per_s': N / (trace_ms * 1e-3)},
             'step_tensor_tflops': flops / (ms * 1e-3) / 1e12, 'cpu_baseline': None}
     if not args.no_cpu:
+        import nero_oracle_mat as OM          # the CPU leg: the oracle port is what is timed here
         Pc = args.cpu_points
         tabs = (OM.direction_samples(512), OM.direction_samples(256))
         bc = {k: v[:Pc].cpu() for k, v in batch.items()}

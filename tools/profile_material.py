@@ -4,8 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'oracle')):
     sys.path.insert(0, p)
 import torch
-import nero_oracle as O
-import nero_oracle_mat as OM
+from nero_b200 import synthetic as O
+from nero_b200 import synthetic as OM
 from nero_b200 import params as PR
 from nero_b200.material import NeROMaterialRenderer
 sys.path.insert(0, os.path.join(ROOT, 'tools'))

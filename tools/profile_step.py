@@ -5,7 +5,7 @@ for p in (ROOT, os.path.join(ROOT, 'oracle')):
     sys.path.insert(0, p)
 import torch
 import bench
-import nero_oracle as O
+from nero_b200 import synthetic as O
 dev = torch.device('cuda')
 net, sd = bench.build_net({}, dev)
 R = int(os.environ.get('RAYS', 1024))
