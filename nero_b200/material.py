@@ -38,6 +38,8 @@ def read_ply(path):
             if line == 'end_header':
                 break
         fmt = [l.split()[1] for l in header if l.startswith('format')][0]
+        if fmt not in ('ascii', 'binary_little_endian'):
+            raise NotImplementedError(f'PLY format {fmt}')
         elems, cur = [], None
         for l in header:
             t = l.split()
