@@ -160,8 +160,9 @@ def run_ours(args):
     for _ in range(args.warmup):
         resident_step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)      # clocks / throttle reasons of rank 0's GPU only (one nvidia-smi poller per job, not per rank)
+    if rank == 0:
+        sampler.start()
     l0 = ops.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -198,7 +199,8 @@ def run_ours(args):
     barrier()
     ms_e2e = ev0.elapsed_time(ev1) / args.steps
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     # ---- roofline of the dominant kernel (tcgen05 linear, N=256 tiles): per-launch CUDA events on the launch stream
     prof = None
