@@ -126,7 +126,9 @@ def run_ours(args):
     bear = args.workload == 'bear'        # BASELINE.json configs[2] / SURVEY 8d config 3: human light on, 2048 rays on one GPU
     cfg = {'shader_config': {'human_light': True}} if bear else {}
     net, sd = build_net(cfg, dev)
-    R = 2048 if bear else RAYS_PER_GPU    # weak scaling: fixed rays per GPU, global batch = R * world
+    # weak scaling: fixed rays per GPU, global batch = R * world.  bear: 2048 rays on one GPU (configs[2]); under torchrun
+    # 1024 per GPU, i.e. 8192 rays on 8 GPUs (configs[4])
+    R = (2048 if world == 1 else 1024) if bear else RAYS_PER_GPU
     rays = synthetic.synthetic_rays(R * world, seed=6033)
     r = {k: v[rank * R:(rank + 1) * R].to(dev).contiguous() for k, v in rays.items()}
     from nero_b200.optim import FlatAdam
@@ -217,7 +219,7 @@ def run_ours(args):
             'metric': 'train rays/sec (128 samples/ray)', 'value': R * world / (ms * 1e-3), 'unit': 'rays/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32 (split-bf16 x3 tensor-core MMAs, fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD.replace('bell', 'bear_human_light').replace('1024rays', '2048rays') if bear else WORKLOAD, 'rays_per_gpu': R, 'global_rays': R * world, 'n_in': n_in, 'n_out': n_out, 'p_occ': p_occ,
+            'config': {'workload': WORKLOAD.replace('bell', 'bear_human_light').replace('1024rays', f'{R}rays') if bear else WORKLOAD, 'rays_per_gpu': R, 'global_rays': R * world, 'n_in': n_in, 'n_out': n_out, 'p_occ': p_occ,
                        'parallelism': f'ray-sharded dp{world}, one NCCL all-reduce of the flat grad buffer' if world > 1 else 'single gpu',
                        'l2': 'per-step working set ~6 GB of activations >> 126 MB L2 (inputs larger than L2)',
                        'optimizer': 'Adam (nero_adam_flat over the flat parameter buffer) inside the timed region'},
