@@ -524,13 +524,17 @@ class ShapeEngine:
             ls = self.sdf.L + [self.sdf.L8f, self.sdf.L8s] + self.nerf.all_layers()
             for m in self.predictors():
                 ls += m.layers
-            self._all_layers = ls
-        ops.prep_batch(self._all_layers)
+            self._all_layers = ops.PrepBatch(ls)
+        self._all_layers.run()
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, R, S):
-        if self.cap == (R, S):
+        """Workspaces only grow: every kernel takes explicit R / S / leading dimensions / row caps, so a smaller batch (the
+        ragged last chunk of an image, a train -> validation switch) runs in the buffers of a larger one."""
+        if R <= self.cap[0] and S <= self.cap[1]:
             return
+        R, S = max(R, self.cap[0]), max(S, self.cap[1])
+        self.w = None                       # release the old workspaces before allocating the larger ones
         dev = self.dev
         cap = R * S
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)

@@ -176,8 +176,8 @@ class MaterialEngine:
             ls = self.feats.L0 + self.feats.L1
             for m in self.predictors():
                 ls += m.layers
-            self._all_layers = ls
-        ops.prep_batch(self._all_layers)
+            self._all_layers = ops.PrepBatch(ls)
+        self._all_layers.run()
 
     # ------------------------------------------------------------------ tracing (renderer.py:719-729)
     def trace(self, rays_o, rays_d):

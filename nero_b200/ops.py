@@ -116,35 +116,43 @@ class PreparedLayer:
 
 
 _PREP_JOB = None
-_prep_cache = {}
 
 
-def prep_batch(layers):
-    """PreparedLayer.prep() of many layers as ONE nero_prep_weight_batch launch.  The job table only holds pointers, so it
-    is built once per set of parameter storages and reused every step."""
-    global _PREP_JOB, launch_count
-    if DRY_RUN or not layers:
-        return
-    import numpy as np
-    if _PREP_JOB is None:
-        _PREP_JOB = np.dtype([('v', 'u8'), ('g', 'u8'), ('kmap', 'u8'), ('img_f', 'u8'), ('img_t', 'u8'), ('w_eff', 'u8'), ('K', 'i4'),
-                              ('row0', 'i4'), ('nrows', 'i4'), ('rows_pad_f', 'i4'), ('rows_pad_t', 'i4'), ('t_c0', 'i4'),
-                              ('t_ncols', 'i4'), ('ld_weff', 'i4'), ('in_scale', 'f4'), ('pad', 'i4')])
-        assert _PREP_JOB.itemsize == 88
-    key = (id(layers[0]), len(layers)) + tuple(l.weight.data_ptr() for l in layers) + tuple(0 if l.g is None else l.g.data_ptr() for l in layers)
-    ent = _prep_cache.get(key[:2])
-    if ent is None or ent[0] != key:
-        ptr = lambda t: 0 if t is None else t.data_ptr()
-        arr = np.zeros(len(layers), dtype=_PREP_JOB)
-        for i, l in enumerate(layers):
-            arr[i] = (ptr(l.weight), ptr(l.g), ptr(l.kmap), ptr(l.img_f), ptr(l.img_t), ptr(l.w_eff), l.K, l.row0, l.nrows, l.n_pad,
-                      l.t_npad if l.img_t is not None else 0, l.t_cols[0] if l.t_cols else 0, l.t_cols[1] if l.t_cols else 0, l.K, 1.0, 0)
-        tab = torch.from_numpy(arr.view(np.uint8).copy()).to(layers[0].img_f.device)
-        ent = (key, tab, int(arr['nrows'].max()))
-        _prep_cache[key[:2]] = ent
-    rc = lib.nero_prep_weight_batch(_ptr(ent[1]), len(layers), ent[2], _stream())
-    _check(rc, 'nero_prep_weight_batch')
-    launch_count += 1
+class PrepBatch:
+    """PreparedLayer.prep() of many layers as ONE nero_prep_weight_batch launch.  The job table only holds device pointers;
+    it is owned by the object that owns the layers (an engine) and is rebuilt whenever ANY pointer it holds changes
+    (parameter storages after .to()/load_state_dict, operand images, kmaps), so a table can never outlive its buffers."""
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+        self.key, self.tab, self.max_rows = None, None, 0
+
+    @staticmethod
+    def _ptrs(l):
+        p = lambda t: 0 if t is None else t.data_ptr()
+        return (p(l.weight), p(l.g), p(l.kmap), p(l.img_f), p(l.img_t), p(l.w_eff))
+
+    def run(self):
+        global _PREP_JOB, launch_count
+        if DRY_RUN or not self.layers:
+            return
+        import numpy as np
+        if _PREP_JOB is None:
+            _PREP_JOB = np.dtype([('v', 'u8'), ('g', 'u8'), ('kmap', 'u8'), ('img_f', 'u8'), ('img_t', 'u8'), ('w_eff', 'u8'), ('K', 'i4'),
+                                  ('row0', 'i4'), ('nrows', 'i4'), ('rows_pad_f', 'i4'), ('rows_pad_t', 'i4'), ('t_c0', 'i4'),
+                                  ('t_ncols', 'i4'), ('ld_weff', 'i4'), ('in_scale', 'f4'), ('pad', 'i4')])
+            assert _PREP_JOB.itemsize == 88
+        key = tuple(self._ptrs(l) for l in self.layers)
+        if key != self.key:
+            arr = np.zeros(len(self.layers), dtype=_PREP_JOB)
+            for i, (l, pt) in enumerate(zip(self.layers, key)):
+                arr[i] = pt + (l.K, l.row0, l.nrows, l.n_pad, l.t_npad if l.img_t is not None else 0, l.t_cols[0] if l.t_cols else 0,
+                               l.t_cols[1] if l.t_cols else 0, l.K, 1.0, 0)
+            self.tab = torch.from_numpy(arr.view(np.uint8).copy()).to(self.layers[0].img_f.device)
+            self.key, self.max_rows = key, int(arr['nrows'].max())
+        rc = lib.nero_prep_weight_batch(_ptr(self.tab), len(self.layers), self.max_rows, _stream())
+        _check(rc, 'nero_prep_weight_batch')
+        launch_count += 1
 
 
 def _m_of(m_ptr, m_cap):

@@ -71,7 +71,11 @@ class NeROShapeRenderer(nn.Module):
         self.color_network = ShadingParams(c['shader_config'])
         self._engine = None
         # extract_mesh.py:27 calls network.sdf_network.sdf(x): route it to the forward-only CUDA chain
-        self.sdf_network.sdf = self._sdf_query
+        # (through a weak reference: a bound method stored on the child module would tie renderer <-> sdf_network into a
+        # reference cycle that keeps the multi-GB workspaces alive until the cyclic GC runs, and would travel with deepcopy)
+        import weakref
+        me = weakref.ref(self)
+        self.sdf_network.sdf = lambda x: me()._sdf_query(x)
         self._weights_dirty = True
         if training:
             self._init_dataset()
@@ -202,10 +206,22 @@ class NeROShapeRenderer(nn.Module):
         self._shuffle_train_batch()
 
     def _shuffle_train_batch(self):
+        """network/renderer.py:161-165.  The shuffled table lives in pinned host memory (train_step copies slices of it with
+        non_blocking H2D); the two pinned buffers per key are allocated once and alternate, instead of re-pinning the
+        whole table on every reshuffle."""
         self.train_batch_i = 0
         idx = torch.randperm(self.tbn, device='cpu')
+        pin = torch.cuda.is_available()
+        spare = getattr(self, '_train_batch_spare', None) or {}
+        new = {}
         for k, v in self.train_batch.items():
-            self.train_batch[k] = v[idx].pin_memory() if torch.cuda.is_available() else v[idx]
+            buf = spare.get(k)
+            if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=pin)
+            torch.index_select(v, 0, idx, out=buf)
+            new[k] = buf
+        self._train_batch_spare = self.train_batch if all(not pin or v.is_pinned() for v in self.train_batch.values()) else {}
+        self.train_batch = new
 
     def _construct_ray_batch(self, imgs_info, device='cpu'):
         imn, _, h, w = imgs_info['imgs'].shape

@@ -130,13 +130,14 @@ def test_wgrad(M, N, K, two):
     assert e_v < 3e-5 and e_g < 3e-5 and e_b < 1e-5
 
 
-def test_chain_matches_layerwise_and_fp64():
+@pytest.mark.parametrize('M', [3000, 45001])
+def test_chain_matches_layerwise_and_fp64(M):
     """Fused chain (A operand in TMEM) vs fp64 torch: 3 softplus layers with the skip-concat, then a linear head;
-    then a derivative (DACT) chain in the reverse direction with addend / tail."""
+    then a derivative (DACT) chain in the reverse direction with addend / tail.  M = 45001 is 352 row tiles: every one of
+    the 148 persistent CTAs loops over at least two tiles (mbarrier phases across tiles) and the last tile is ragged."""
     from nero_b200 import ops
     from nero_b200.ops import Mat, chain, chain_layer as CL
     dev = torch.device('cuda')
-    M = 3000
     L0, W0, b0 = _mk_layer(ops, 256, 39, dev, seed=1, t_cols=(0, 39))
     L1, W1, b1 = _mk_layer(ops, 217, 256, dev, seed=2, t_cols=(0, 256))
     L2, W2, b2 = _mk_layer(ops, 256, 256, dev, seed=3, t_cols=(0, 256))
@@ -180,6 +181,49 @@ def test_chain_matches_layerwise_and_fp64():
         e = float((got.double() - want).abs().max())
         print(f'chain dact {nm}: max abs err {e:.2e} (|want| max {float(want.abs().max()):.2e})')
         assert e < 3e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize('M', [1500, 40007])
+def test_tangent_chain_matches_fp64(M):
+    """Tangent-sweep chain (EK_TANGENT: out = s*acc, out2 = 100*(1-s)*V*acc with s = sigma(100 a) recovered from the stored
+    softplus output) over three layers incl. the skip-concat split, vs fp64 torch; M = 40007 gives every CTA >= 2 tiles."""
+    from nero_b200 import ops
+    from nero_b200.ops import Mat, chain, chain_layer as CL
+    dev = torch.device('cuda')
+    L0, W0, _ = _mk_layer(ops, 256, 39, dev, seed=11)
+    L1, W1, _ = _mk_layer(ops, 217, 256, dev, seed=12)
+    L2, W2, _ = _mk_layer(ops, 256, 256, dev, seed=13)
+    g = torch.Generator().manual_seed(M)
+    U0 = torch.zeros(M, 64, device=dev)
+    U0[:, :39] = torch.randn(M, 39, generator=g).to(dev)
+    H = [(torch.rand(M, 256, generator=g) * 0.04).to(dev) for _ in range(3)]
+    V = [torch.randn(M, 256, generator=g).to(dev) for _ in range(3)]
+    UB = [torch.zeros(M, 256, device=dev) for _ in range(3)]
+    AB = [torch.zeros(M, 256, device=dev) for _ in range(3)]
+    skip = torch.randn(M, 39, generator=g).to(dev)
+    UB[1][:, 217:] = skip                                   # tangent of the PE/sqrt2 tail, pre-stored like pe_tangent does
+    chain(Mat(U0), 40, [CL(L0, ops.EK_TANGENT, 256, use_bias=False, H=Mat(H[0]), V=Mat(V[0]), out2=Mat(AB[0]), save=Mat(UB[0])),
+                        CL(L1, ops.EK_TANGENT, 217, use_bias=False, oscale=0.70710678, H=Mat(H[1]), hscale=1.41421356, V=Mat(V[1]),
+                           out2=Mat(AB[1]), save=Mat(UB[1]), csrc=Mat(UB[1])),
+                        CL(L2, ops.EK_TANGENT, 256, use_bias=False, H=Mat(H[2]), V=Mat(V[2]), out2=Mat(AB[2]), save=Mat(UB[2]))])
+    torch.cuda.synchronize()
+    s0 = ops._dact(H[0].double(), 1)
+    a0 = U0[:, :39].double() @ W0.t()
+    u1 = s0 * a0
+    q0 = 100 * (1 - s0) * V[0].double() * a0
+    s1 = ops._dact(H[1].double()[:, :217] * 1.41421356, 1)
+    a1 = u1 @ W1.t()
+    u2 = torch.cat([0.70710678 * s1 * a1, skip.double()], -1)
+    q1 = 100 * (1 - s1) * V[1].double()[:, :217] * a1
+    s2 = ops._dact(H[2].double(), 1)
+    a2 = u2 @ W2.t()
+    u3 = s2 * a2
+    q2 = 100 * (1 - s2) * V[2].double() * a2
+    for nm, got, want in [('u1', UB[0], u1), ('q0', AB[0], q0), ('u2', UB[1], u2), ('q1', AB[1][:, :217], q1), ('u3', UB[2], u3), ('q2', AB[2], q2)]:
+        e = float((got.double() - want).abs().max())
+        sc = max(1.0, float(want.abs().max()))
+        print(f'tangent chain {nm} (M={M}): max abs err {e:.2e} (|want| max {sc:.2e})')
+        assert e < 3e-5 * sc, nm
 
 
 def test_flat_adam_matches_torch_adam():

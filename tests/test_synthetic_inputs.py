@@ -28,8 +28,8 @@ def test_measured_arms_do_not_import_the_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = open(os.path.join(root, 'bench.py')).read()
     tree = ast.parse(src)
-    fns = {n.name: n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)}
-    for name in ('run_ours', 'build_net', 'synthetic_dataset', 'profile_linear', 'training_loss'):
+    fns = {n.name: n for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+    for name in ('run_ours', 'build_net', 'synthetic_dataset', 'profile_chains', 'training_loss', 'Workload', 'timed'):
         body = ast.get_source_segment(src, fns[name])
         assert 'nero_oracle' not in body, f'bench.py:{name} must not use the oracle'
     assert 'nero_oracle' in ast.get_source_segment(src, fns['cpu_baseline'])     # the one leg that times it
