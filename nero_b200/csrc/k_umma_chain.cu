@@ -5,29 +5,37 @@
 //     [  0,256)  fp32 accumulator of the current layer (D operand)
 //     [256,384)  A operand, bf16 "hi" plane, two K elements per 32-bit column  (A read by tcgen05.mma FROM TMEM)
 //     [384,512)  A operand, bf16 "lo" plane                                    (split-bf16: x ~= hi + lo)
-//   Per layer: the MMA warp issues, per 16-wide k-step, A_lo*W_hi + A_hi*W_lo + A_hi*W_hi into the accumulator;
-//   twelve epilogue warps then read the accumulator (tcgen05.ld), apply bias/activation or the derivative products
-//   of the gradient sweeps, store what the backward pass needs to HBM (coalesced through a per-warp transpose
-//   buffer) and write the NEXT layer's A operand straight back into TMEM (tcgen05.st) as packed split-bf16.
-//   Weights stream from L2 as pre-swizzled images (one cp.async.bulk per 64-wide K chunk, 3-stage mbarrier ring).
-//   Aux operands of the derivative epilogues (H, addend, V) are prefetched into L2 one layer ahead.
+//   Per layer: the MMA warp issues, per 16-wide k-step, A_lo*W_hi + A_hi*W_lo + A_hi*W_hi into the accumulator; the
+//   epilogue warps then read the accumulator (tcgen05.ld, one matrix row per thread), apply bias/activation or the
+//   derivative products of the gradient sweeps, and write the NEXT layer's A operand straight back into TMEM
+//   (tcgen05.st) as packed split-bf16.
 //
-// This realises SURVEY.md K2/K3/K4/K10/K13 "activations stay on-chip across layers": compared with one
-// nero_linear launch per layer it removes the A-operand HBM round trip (1 KB/sample/layer) and the producer
-// load->convert->store latency chain, which the ncu profiles of round 1 (profiles/r01b_*) show to dominate.
+//   Round 2 (v3): every HBM operand of the epilogue moves through TMA.  The epilogue warps form TEAMS of four warps (one
+//   per TMEM lane quarter); a team works on [128 rows x 16 columns] units.  Per team a FIFO of 8 KB shared-memory slots
+//   (SWIZZLE_64B boxes, bank-conflict free for one-row-per-thread 16-byte accesses) is filled by cp.async.bulk.tensor
+//   loads that the team's leader thread issues up to kSlotsIn units AHEAD -- across units, layers and tiles, i.e. while
+//   the tensor core is still busy with the MMAs whose epilogue will consume them -- and results leave through
+//   cp.async.bulk.tensor stores from kSlotsOut staging slots.  No thread ever waits on a global load; the former
+//   long-scoreboard stalls (ncu, round 1: 6.6 of 12.3 cycles per issued instruction) are gone.
+//   Weights stream from L2 as pre-swizzled images: one stage = the hi and lo planes of one 64-wide K chunk for one
+//   half of the N range (32 KB, cp.async.bulk, 4-stage mbarrier ring).
 //
-// Skip connection of the SDF network (field.py:139-140): a layer with `concat` set takes columns >= ncol_out of the
-// next A operand from its own `save` buffer, where ray_fill / pe_tangent pre-stored PE/sqrt2 resp. its tangent.
-#include "umma_common.cuh"
+// This realises SURVEY.md K2/K3/K4/K10/K13 "activations stay on-chip across layers".
+//
+// Skip connection of the SDF network (field.py:139-140): a layer with `csrc` set takes columns >= ncol_out of the
+// next A operand from that buffer, where ray_fill / pe_tangent pre-stored PE/sqrt2 resp. its tangent.
+#include <cuda.h>
 
-#ifndef NERO_EARLY_ISSUE
-#define NERO_EARLY_ISSUE 0   // issue all aux-operand loads of a block before reading the accumulator
-#endif
+#include <mutex>
+#include <unordered_map>
+
+#include "umma_common.cuh"
 
 namespace nero {
 
 constexpr int kMaxChainLayers = 10;
 
+// ---------------------------------------------------------------------------------------------- C ABI (host) structs
 struct ChainLayer {
   const uint8_t* wimg; const float* bias;
   float* save; const float* H; const float* addend; const float* V; float* out2; float* tail;
@@ -44,32 +52,47 @@ struct ChainParams {
   ChainLayer L[kMaxChainLayers];
 };
 
+// ---------------------------------------------------------------------------------------------- device-side records
+enum ChainOp : int { OP_H = 0, OP_AUX2 = 1, OP_CSRC = 2, OP_SAVE = 3, OP_OUT2 = 4, OP_COUNT = 5 };
+
+struct ChainLayerDev {
+  const uint8_t* wimg; const float* bias;
+  float* save; const float* H; const float* aux2; float* out2; float* tail; const float* csrc;
+  int n_pad, k_chunks, n_bias, ncol_out, ncol_main, kind, act;
+  int ld_save, ldh, ld2, ldo2, ldt, ld_csrc;
+  float oscale, hscale, act_param;
+  int write_a, a_blocks;
+  int aux2_is_addend;          // aux2 = addend (derivative kinds) or V (tangent kind)
+  int tma;                     // bit o set: operand o moves through TMA (tensor map maps[map[o]])
+  int map[OP_COUNT];
+  int n_units;                 // 16-column units the epilogue walks (accumulator columns + next-A columns to define)
+};
+constexpr int kMaxMaps = 1 + kMaxChainLayers * OP_COUNT;
+struct ChainParamsDev {
+  const float* A0; int lda0; int k_valid0; int a0_tma; int a0_units;
+  int n_layers; const int* m_ptr; int m_cap;
+  ChainLayerDev L[kMaxChainLayers];
+  CUtensorMap maps[kMaxMaps];        // maps[0]: A0
+};
+
+// ---------------------------------------------------------------------------------------------- configuration
 constexpr int CH_BM = 128, CH_BK = 64;
-constexpr int kChEpiWarps = 12;
+constexpr int kTeams = 2;                          // epilogue teams (4 warps each, one per TMEM lane quarter)
+constexpr int kChEpiWarps = 4 * kTeams;
 constexpr int kChMmaWarp = kChEpiWarps, kChLoadWarp = kChEpiWarps + 1;
 constexpr int kChThreads = (kChEpiWarps + 2) * 32;
-#ifndef NERO_EPI_V2
-#define NERO_EPI_V2 1
-#endif
-// NERO_NSPLIT=1 (needs the v2 epilogue): layers wider than 128 columns run as two N halves so that the epilogue of half 0
-// overlaps the MMAs of half 1.  Measured on B200 (round 1): 15.6 -> 16.0-16.5 ms/step, i.e. a LOSS -- the epilogue of half
-// 0 may not overwrite the A operand in TMEM before the half-1 MMAs have read it (a_free barrier), N=128 MMAs have less
-// reuse of the A operand, and the epilogue, not the MMA, is the longer phase.  Kept for experiments, off by default.
-#ifndef NERO_NSPLIT
-#define NERO_NSPLIT 0
-#endif
-#if NERO_NSPLIT
-constexpr int kChStages = 6;
-constexpr uint32_t kChStageBytes = 2 * 128 * 128;                       // half a W chunk: hi + lo planes of up to 128 rows
-#else
-constexpr int kChStages = 3;
-constexpr uint32_t kChStageBytes = 2 * 256 * 128;                       // W chunk: hi + lo planes of up to 256 rows
-#endif
-constexpr uint32_t kChEpiBytes = kChEpiWarps * kStageWarpBytes;         // 30 KB
+constexpr int kWStages = 4;
+constexpr uint32_t kWStageBytes = 2 * 128 * 128;   // hi + lo planes of up to 128 weight rows x 64 K
+constexpr int kSlotsIn = 4, kSlotsOut = 2;         // per team
+constexpr uint32_t kSlotBytes = CH_BM * 16 * 4;    // [128 rows x 16 fp32] = 8 KB
+constexpr uint32_t kSlotsBytes = kTeams * (kSlotsIn + kSlotsOut) * kSlotBytes;
 constexpr uint32_t kChBiasBytes = 2 * 256 * 4;
-constexpr uint32_t kChSmemBytes = kChStages * kChStageBytes + kChEpiBytes + kChBiasBytes + 1024 + 256;
+constexpr uint32_t kChBarBytes = 512;
+constexpr uint32_t kChSmemBytes = kWStages * kWStageBytes + kSlotsBytes + kChBiasBytes + kChBarBytes;
+static_assert(kChSmemBytes <= 232448, "shared memory budget");
 constexpr uint32_t kAccCol = 0, kAHiCol = 256, kALoCol = 384;
 
+// ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -87,6 +110,24 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+// TMA: 2-D tiled load global -> shared (arrives on an mbarrier with the box byte count), store shared -> global
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int r0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(r0)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int r0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(r0)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 2) : "memory"); }
+
 // write 16 fp32 values of this lane's row (columns c0..c0+15 of the next A operand) as packed split-bf16 into TMEM
 __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const float* y) {
   uint32_t hi[8], lo[8];
@@ -96,331 +137,320 @@ __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const
   tmem_st8(tmem_lane_base + kALoCol + (c0 >> 1), lo);
 }
 
-template <int KIND>
-__device__ __forceinline__ void chain_epilogue_layer(const ChainLayer& L, uint32_t tmem_lane_base, int row0, int rows_valid,
-                                                     int third, int lane, float* stg, const float* s_bias) {
-  constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
-  const int nblk = L.n_pad >> 4;
-  const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
-  const bool v_save = L.save && vec_ok(L.save, L.ld_save);
-  // when this layer feeds the next one, every 16-column block the next layer's MMAs read must be defined
-  const int nblk_a = L.write_a ? max(L.a_blocks, nblk) : 0;
-  const int nb_loop = max(nblk, nblk_a);
-#pragma unroll 1
-  for (int b = third; b < nb_loop; b += 3) {
-    const int c0 = b * 16;
-    float r[16];
-    if (b < nblk && c0 < L.ncol_out) {
-      float v[16];
-      const int cm = nmain - c0;   // main columns in this block (may be <= 0)
-#if NERO_EARLY_ISSUE
-      float4 hraw[4], araw[4], vraw[4];
-      if constexpr (!kBias) {      // all aux loads of this block are in flight before the accumulator is read
-        if constexpr (KIND != EK_DACT_NONE) issue_block16(L.H + size_t(row0) * L.ldh + c0, L.ldh, rows_valid, cm, vec_ok(L.H, L.ldh), lane, hraw);
-        if (L.addend) issue_block16(L.addend + size_t(row0) * L.ldadd + c0, L.ldadd, rows_valid, cm, vec_ok(L.addend, L.ldadd), lane, araw);
-        if constexpr (KIND == EK_TANGENT) issue_block16(L.V + size_t(row0) * L.ldv + c0, L.ldv, rows_valid, cm, vec_ok(L.V, L.ldv), lane, vraw);
-      }
-#endif
-      tmem_ld16(tmem_lane_base + kAccCol + c0, v);
-      tmem_ld_wait();
-      if constexpr (kBias) {
+// one row (this thread's) of a [128 x 16] fp32 slot in the SWIZZLE_64B layout: 64-byte rows, the 16-byte chunk index is
+// XORed with bits 1..2 of the row (the pattern cuTensorMapEncodeTiled(..., SWIZZLE_64B) uses; slots are 1024-B aligned)
+__device__ __forceinline__ void slot_read16(const uint8_t* slot, int row, float* x) {
+  const uint8_t* base = slot + row * 64;
+  const int sw = (row >> 1) & 3;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
-        if constexpr (KIND == EK_BIAS_SOFTPLUS) softplus100_fast16(v);
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(base + ((j ^ sw) << 4));
+    x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void slot_write16(uint8_t* slot, int row, const float* x) {
+  uint8_t* base = slot + row * 64;
+  const int sw = (row >> 1) & 3;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float y = v[j];
-          if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
-          else if constexpr (KIND == EK_BIAS_GENERIC) y = apply_act(y, L.act, L.act_param);
-          r[j] = L.oscale * y;
-        }
-      } else {
-        float s[16];
-        if constexpr (KIND == EK_DACT_NONE) {
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4*>(base + ((j ^ sw) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+}
+// direct (non-TMA) access of this thread's row: narrow / unaligned operands and the ragged last tile
+__device__ __forceinline__ void row_load16(const float* __restrict__ g, int ld, long row, int c0, int ncols, bool row_ok, float* x) {
+  const float* p = g + row * ld + c0;
+  const bool vec = row_ok && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s[j] = 1.0f;
-        } else {
-#if NERO_EARLY_ISSUE
-          finish_block16(hraw, stg, lane, s);
-#else
-          load_block16(L.H + size_t(row0) * L.ldh + c0, L.ldh, rows_valid, cm, vec_ok(L.H, L.ldh), stg, lane, s);
-#endif
-          if constexpr (KIND == EK_DACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
-          } else {
-            dsoftplus100_from_h_fast16(s, L.hscale);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = L.oscale * s[j] * v[j];
-        if (L.addend) {
-          float a[16];
-#if NERO_EARLY_ISSUE
-          finish_block16(araw, stg, lane, a);
-#else
-          load_block16(L.addend + size_t(row0) * L.ldadd + c0, L.ldadd, rows_valid, cm, vec_ok(L.addend, L.ldadd), stg, lane, a);
-#endif
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] += a[j];
-        }
-        if (L.tail && c0 + 16 > L.ncol_main) {
-          const int shift = max(L.ncol_main - c0, 0);
-          const int ncols = min(16, L.ncol_out - c0);
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j >= shift && j < ncols && lane < rows_valid)
-              L.tail[size_t(row0 + lane) * L.ldt + (c0 + j - L.ncol_main)] = L.oscale * v[j];
-        }
-        if constexpr (KIND == EK_TANGENT) {
-          float vv[16];
-#if NERO_EARLY_ISSUE
-          finish_block16(vraw, stg, lane, vv);
-#else
-          load_block16(L.V + size_t(row0) * L.ldv + c0, L.ldv, rows_valid, cm, vec_ok(L.V, L.ldv), stg, lane, vv);
-#endif
-          if (cm > 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) vv[j] = 100.0f * (1.0f - s[j]) * vv[j] * v[j];
-            store_block16(L.out2 + size_t(row0) * L.ldo2 + c0, L.ldo2, rows_valid, cm, vec_ok(L.out2, L.ldo2), stg, lane, vv);
-          }
-        }
-      }
-      if (L.save && nmain - c0 > 0) store_block16(L.save + size_t(row0) * L.ld_save + c0, L.ld_save, rows_valid, nmain - c0, v_save, stg, lane, r);
+  for (int j = 0; j < 4; ++j) {
+    if (vec && 4 * j + 3 < ncols) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + 4 * j));
+      x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = 0.0f;
-    }
-    if (b < nblk_a) {
-      // columns >= nmain of the next A operand: the skip-concat source (from the save buffer) or zero
-      if (c0 + 16 > nmain) {
-        float cc[16];
-        if (L.csrc) load_block16(L.csrc + size_t(row0) * L.ld_csrc + c0, L.ld_csrc, rows_valid, 256 - c0, vec_ok(L.csrc, L.ld_csrc), stg, lane, cc);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j >= nmain) r[j] = L.csrc ? cc[j] : 0.0f;
-      }
-      write_a16(tmem_lane_base, c0, r);
+      for (int i = 0; i < 4; ++i) x[4 * j + i] = (row_ok && 4 * j + i < ncols) ? __ldg(p + 4 * j + i) : 0.0f;
     }
   }
 }
-
-// ------------------------------------------------------------------------------------------------------------------
-// Epilogue v2: accumulator fragments in the 16x256b TMEM load shape (thread t of a warp holds, per 8-column repeat,
-// columns 2(t%4), 2(t%4)+1 of rows t/4 and t/4+8 -- the m16n8 fragment).  A quad then covers 32 contiguous bytes of one
-// matrix row, so aux operands (H, addend, V) are read and results written DIRECTLY from/to global memory with full
-// 32-byte sectors: no shared-memory transposes, no warp syncs, and the loads are in flight before the accumulator
-// read completes.  The packed split-bf16 A operand of the next layer is one 32-bit word per (row, column pair) = the
-// 16x128b store shape with the same thread <-> (row, column) map.
-#ifndef NERO_EPI_V2
-#define NERO_EPI_V2 1
-#endif
-
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-
-// element e = 4j + 2hh + q of a [16 rows x 32 cols] unit  <->  row rlo + 8hh, column c0 + 8j + 2a + q
-struct FragPos { int rlo; int a; bool plo, phi; };
-
-__device__ __forceinline__ bool vec2_ok(const float* p, int ld) {
-  return ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(p) & 7) == 0);
-}
-// g: matrix origin (row 0, first column of the layer window); columns >= ncols and masked rows read as zero
-__device__ __forceinline__ void frag_load(const float* __restrict__ g, int ld, const FragPos& f, int c0, int ncols, bool v2, float* x) {
+__device__ __forceinline__ void row_store16(float* __restrict__ g, int ld, long row, int c0, int ncols, bool row_ok, const float* x) {
+  if (!row_ok) return;
+  float* p = g + row * ld + c0;
+  const bool vec = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int col = c0 + 8 * j + 2 * f.a;
+    if (vec && 4 * j + 3 < ncols) {
+      *reinterpret_cast<float4*>(p + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    } else {
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float2 val = make_float2(0.f, 0.f);
-      if ((hh ? f.phi : f.plo) && col < ncols) {
-        const float* p = g + size_t(f.rlo + 8 * hh) * ld + col;
-        if (v2 && col + 1 < ncols) val = *reinterpret_cast<const float2*>(p);
-        else { val.x = p[0]; if (col + 1 < ncols) val.y = p[1]; }
-      }
-      x[4 * j + 2 * hh] = val.x; x[4 * j + 2 * hh + 1] = val.y;
+      for (int i = 0; i < 4; ++i)
+        if (4 * j + i < ncols) p[4 * j + i] = x[4 * j + i];
     }
   }
-}
-__device__ __forceinline__ void frag_store(float* __restrict__ g, int ld, const FragPos& f, int c0, int ncols, bool v2, const float* x) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int col = c0 + 8 * j + 2 * f.a;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      if ((hh ? f.phi : f.plo) && col < ncols) {
-        float* p = g + size_t(f.rlo + 8 * hh) * ld + col;
-        if (v2 && col + 1 < ncols) *reinterpret_cast<float2*>(p) = make_float2(x[4 * j + 2 * hh], x[4 * j + 2 * hh + 1]);
-        else { p[0] = x[4 * j + 2 * hh]; if (col + 1 < ncols) p[1] = x[4 * j + 2 * hh + 1]; }
-      }
-    }
-  }
-}
-// next layer's A operand: 32 columns of this unit as packed split-bf16 (16 packed columns per plane)
-__device__ __forceinline__ void frag_write_a(uint32_t tl, int c0, const float* r) {
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    split2(r[4 * j], r[4 * j + 1], hi[2 * j], lo[2 * j]);              // row t/4
-    split2(r[4 * j + 2], r[4 * j + 3], hi[2 * j + 1], lo[2 * j + 1]);  // row t/4 + 8
-  }
-  tmem_st_16x128b_x4(tl + kAHiCol + (c0 >> 1), hi);
-  tmem_st_16x128b_x4(tl + kALoCol + (c0 >> 1), lo);
 }
 
+// ---------------------------------------------------------------------------------------------- unit bookkeeping
+// Which TMA loads unit u of layer record `li` needs (li = -1: the tile's first A operand).  The leader (producer side)
+// and every thread (consumer side) of a team evaluate the same function, so the FIFO order is implied.
+__device__ __forceinline__ int layer_nmain(const ChainLayerDev& L) {
+  return (L.kind <= EK_BIAS_GENERIC) ? L.ncol_out : min(L.ncol_out, L.ncol_main);
+}
+__device__ __forceinline__ uint32_t unit_in_mask(const ChainParamsDev& p, int li, int u) {
+  if (li < 0) return p.a0_tma ? 1u : 0u;
+  const ChainLayerDev& L = p.L[li];
+  const int c0 = u * 16, nblk = L.n_pad >> 4, nmain = layer_nmain(L);
+  uint32_t m = 0;
+  if (u < nblk && c0 < L.ncol_out && c0 < nmain) {
+    if (L.kind >= EK_DACT_SOFTPLUS && L.kind != EK_DACT_NONE && L.H) m |= 1u << OP_H;
+    if (L.aux2) m |= 1u << OP_AUX2;
+  }
+  if (L.write_a && L.csrc && c0 + 16 > nmain) m |= 1u << OP_CSRC;
+  return m & uint32_t(L.tma);
+}
+__device__ __forceinline__ int units_of(const ChainParamsDev& p, int li) { return li < 0 ? p.a0_units : p.L[li].n_units; }
+
+// FIFO position of a team: (tile, layer record, unit, operand)
+struct FifoCursor {
+  int tile, li, u, op;
+  uint32_t seq;       // loads issued / consumed so far
+};
+// advance `c` to the next TMA load at or after its position; returns false when the tile loop is exhausted
+__device__ __forceinline__ bool cursor_seek(const ChainParamsDev& p, FifoCursor& c, int team, int num_tiles, int tile_step) {
+  while (c.tile < num_tiles) {
+    while (c.li < p.n_layers) {
+      const int nu = units_of(p, c.li);
+      while (c.u < nu) {
+        const uint32_t m = unit_in_mask(p, c.li, c.u);
+        while (c.op < 3) {
+          if (m & (1u << c.op)) return true;
+          ++c.op;
+        }
+        c.op = 0;
+        c.u += kTeams;
+      }
+      ++c.li;
+      c.u = team;
+    }
+    c.tile += tile_step;
+    c.li = -1;
+    c.u = team;
+  }
+  return false;
+}
+
+struct TeamCtx {
+  uint8_t* slots_in;        // kSlotsIn x 8 KB
+  uint8_t* slots_out;       // kSlotsOut x 8 KB
+  uint64_t* full;           // [kSlotsIn]
+  uint64_t* out_free;       // leader -> team: the staging slots of the coming unit have been read by their TMA stores
+  int team, q, lane;
+  bool leader;
+  uint32_t cons_seq;        // loads consumed so far (all threads)
+  uint32_t out_phase;       // parity of out_free
+  uint32_t out_units;       // units with TMA stores so far
+  int last_out_n;           // number of TMA stores of the previous such unit
+  FifoCursor prod;          // leader only
+  bool prod_live;
+};
+
+// leader: issue loads until the FIFO holds kSlotsIn entries beyond `cons_seq`
+__device__ __forceinline__ void fifo_fill(const ChainParamsDev& p, TeamCtx& t, int num_tiles, int tile_step) {
+  while (t.prod_live && t.prod.seq < t.cons_seq + kSlotsIn) {
+    if (!cursor_seek(p, t.prod, t.team, num_tiles, tile_step)) { t.prod_live = false; break; }
+    const int s = t.prod.seq % kSlotsIn;
+    const CUtensorMap* map = t.prod.li < 0 ? &p.maps[0] : &p.maps[p.L[t.prod.li].map[t.prod.op]];
+    mbar_arrive_expect_tx(&t.full[s], kSlotBytes);
+    tma_load_2d(t.slots_in + s * kSlotBytes, map, t.prod.u * 16, t.prod.tile * CH_BM, &t.full[s]);
+    ++t.prod.seq;
+    ++t.prod.op;
+  }
+}
+// all threads: wait for the next FIFO entry and return its slot
+__device__ __forceinline__ const uint8_t* fifo_pop(TeamCtx& t) {
+  const uint32_t s = t.cons_seq % kSlotsIn;
+  mbar_wait(&t.full[s], (t.cons_seq / kSlotsIn) & 1);
+  ++t.cons_seq;
+  return t.slots_in + s * kSlotBytes;
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue of one unit
 template <int KIND>
-__device__ __forceinline__ void chain_epilogue_layer2(const ChainLayer& L, uint32_t tmem_base, int lg, int grp_row0, int rows_valid,
-                                                      int third, int lane, const float* s_bias, uint64_t* acc_ready1, uint64_t* a_free, uint32_t phase1) {
+__device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx& t, uint32_t tl, int u, int tile,
+                                         int rows_valid, bool tma_store_ok, const float* s_bias, int num_tiles, int tile_step) {
+  const ChainLayerDev& L = p.L[l];
   constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
+  const int c0 = u * 16;
+  const int nblk = L.n_pad >> 4;
   const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
-  const int ncols_a = L.write_a ? max(L.a_blocks * 16, L.n_pad) : 0;     // columns of the next A operand to define
-  const int n_units = ((max(L.n_pad, ncols_a) + 31) >> 5) * 2;
-  const bool v2_save = L.save && vec2_ok(L.save, L.ld_save);
-#pragma unroll 1
-  for (int u = third; u < n_units; u += 3) {
-    const int h = u & 1, c0 = (u >> 1) * 32;
-    if (acc_ready1 && c0 >= 128) {      // second N half of the accumulator: its MMAs ran while half 0 was processed
-      mbar_wait(acc_ready1, phase1);
-      tcgen05_fence_after();
-      acc_ready1 = nullptr;
+  const int nblk_a = L.write_a ? max(L.a_blocks, nblk) : 0;
+  const int rl = t.q * 32 + t.lane;                 // row of this thread inside the tile
+  const long row = long(tile) * CH_BM + rl;
+  const bool row_ok = rl < rows_valid;
+  const uint32_t in_mask = unit_in_mask(p, l, u);
+  const bool computed = u < nblk && c0 < L.ncol_out;
+  const bool has_main = computed && c0 < nmain;
+  const bool st_save = has_main && L.save != nullptr;
+  const bool st_out2 = (KIND == EK_TANGENT) && has_main;
+  const bool tma_save = st_save && (L.tma & (1 << OP_SAVE)) && tma_store_ok;
+  const bool tma_out2 = st_out2 && (L.tma & (1 << OP_OUT2)) && tma_store_ok;
+  const int n_tma_out = int(tma_save) + int(tma_out2);
+  // the staging slots this unit writes must have been read by the TMA stores of earlier units: the leader waits
+  // (bulk-group read completion) and signals the team
+  if (n_tma_out) {
+    if (t.leader) {
+      // single-output units alternate between the two slots (one earlier store may still be reading the other slot);
+      // a unit that fills both slots, or follows one that did, needs every earlier store read
+      if (n_tma_out == 1 && t.last_out_n == 1) tma_wait_read<kSlotsOut - 1>(); else tma_wait_read<0>();
+      mbar_arrive(t.out_free);
     }
-    const int rl = h * 16 + (lane >> 2);
-    FragPos f;
-    f.rlo = grp_row0 + rl; f.a = lane & 3; f.plo = rl < rows_valid; f.phi = rl + 8 < rows_valid;
-    const uint32_t tl = tmem_base + (uint32_t(lg * 32 + h * 16) << 16);
-    float r[16];
-    if (c0 < L.ncol_out) {
-      float v[16];
-      if constexpr (kBias) {
-        tmem_ld_16x256b_x4(tl + kAccCol + c0, v);
-        tmem_ld_wait();
+  }
+  float r[16];
+  float q2[16];
+  if (computed) {
+    float v[16];
+    tmem_ld16(tl + kAccCol + c0, v);
+    if constexpr (kBias) {
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 b = *reinterpret_cast<const float2*>(s_bias + ((c0 + 8 * j + 2 * f.a) & 255));
-          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.x; v[4 * j + 3] += b.y;
-        }
-        if constexpr (KIND == EK_BIAS_SOFTPLUS) softplus100_fast16(v);
+      for (int j = 0; j < 16; ++j) v[j] += s_bias[c0 + j];
+      if constexpr (KIND == EK_BIAS_SOFTPLUS) softplus100_fast16(v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float y = v[e];
-          if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
-          else if constexpr (KIND == EK_BIAS_GENERIC) y = apply_act(y, L.act, L.act_param);
-          r[e] = y;
-        }
-        if (L.oscale != 1.0f) {
+      for (int j = 0; j < 16; ++j) {
+        float y = v[j];
+        if constexpr (KIND == EK_BIAS_RELU) y = fmaxf(y, 0.0f);
+        else if constexpr (KIND == EK_BIAS_GENERIC) y = apply_act(y, L.act, L.act_param);
+        r[j] = y;
+      }
+      if (L.oscale != 1.0f) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] *= L.oscale;
-        }
+        for (int j = 0; j < 16; ++j) r[j] *= L.oscale;
+      }
+    } else {
+      float s[16];
+      if constexpr (KIND == EK_DACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = 1.0f;
       } else {
-        float s[16];
-        if constexpr (KIND != EK_DACT_NONE) frag_load(L.H, L.ldh, f, c0, nmain, vec2_ok(L.H, L.ldh), s);   // in flight during the TMEM read
-        tmem_ld_16x256b_x4(tl + kAccCol + c0, v);
-        tmem_ld_wait();
-        if constexpr (KIND == EK_DACT_NONE) {
+        if (in_mask & (1u << OP_H)) slot_read16(fifo_pop(t), rl, s);
+        else if (has_main) row_load16(L.H, L.ldh, row, c0, nmain - c0, row_ok, s);
+        else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) s[e] = 1.0f;
-        } else if constexpr (KIND == EK_DACT_RELU) {
+          for (int j = 0; j < 16; ++j) s[j] = 0.0f;
+        }
+        if constexpr (KIND == EK_DACT_RELU) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) s[e] = s[e] > 0.0f ? 1.0f : 0.0f;
+          for (int j = 0; j < 16; ++j) s[j] = s[j] > 0.0f ? 1.0f : 0.0f;
         } else {
           dsoftplus100_from_h_fast16(s, L.hscale);
         }
+        if (!has_main) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = s[e] * v[e];
-        if (L.oscale != 1.0f) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] *= L.oscale;
-        }
-        if (L.addend) {
-          float ad[16];
-          frag_load(L.addend, L.ldadd, f, c0, nmain, vec2_ok(L.addend, L.ldadd), ad);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] += ad[e];
-        }
-        if (L.tail && c0 + 32 > L.ncol_main) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int col = c0 + 8 * (e >> 2) + 2 * f.a + (e & 1);
-            const bool pr = (e & 2) ? f.phi : f.plo;
-            if (pr && col >= L.ncol_main && col < L.ncol_out)
-              L.tail[size_t(f.rlo + ((e & 2) ? 8 : 0)) * L.ldt + (col - L.ncol_main)] = L.oscale * v[e];
-          }
-        }
-        if constexpr (KIND == EK_TANGENT) {
-          float vv[16];
-          frag_load(L.V, L.ldv, f, c0, nmain, vec2_ok(L.V, L.ldv), vv);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) vv[e] = 100.0f * (1.0f - s[e]) * vv[e] * v[e];
-          frag_store(L.out2, L.ldo2, f, c0, nmain, vec2_ok(L.out2, L.ldo2), vv);
+          for (int j = 0; j < 16; ++j) s[j] = 0.0f;
         }
       }
-      if (L.save) frag_store(L.save, L.ld_save, f, c0, nmain, v2_save, r);
+      float a2[16];
+      const bool has2 = has_main && L.aux2 != nullptr;
+      if (in_mask & (1u << OP_AUX2)) slot_read16(fifo_pop(t), rl, a2);
+      else if (has2) row_load16(L.aux2, L.ld2, row, c0, nmain - c0, row_ok, a2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = s[j] * v[j];
+      if (L.oscale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] *= L.oscale;
+      }
+      if constexpr (KIND == EK_TANGENT) {
+        if (has_main) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) q2[j] = 100.0f * (1.0f - s[j]) * a2[j] * v[j];
+        }
+      } else {
+        if (has2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] += a2[j];
+        }
+      }
+      if (L.tail && c0 + 16 > L.ncol_main && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          if (col >= L.ncol_main && col < L.ncol_out) L.tail[row * L.ldt + (col - L.ncol_main)] = L.oscale * v[j];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = 0.0f;
+  }
+  // ---- next A operand
+  if (u < nblk_a) {
+    if (c0 + 16 > nmain) {     // columns >= nmain: the skip-concat source or zero
+      float cc[16];
+      if (in_mask & (1u << OP_CSRC)) slot_read16(fifo_pop(t), rl, cc);
+      else if (L.csrc) row_load16(L.csrc, L.ld_csrc, row, c0, 256 - c0, row_ok, cc);
+      float a[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = (c0 + j >= nmain) ? (L.csrc ? cc[j] : 0.0f) : r[j];
+      write_a16(tl, c0, a);
     } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) r[e] = 0.0f;
+      write_a16(tl, c0, r);
     }
-    if (c0 < ncols_a) {
-      if (c0 + 32 > nmain) {   // columns >= nmain: the skip-concat source (from the save buffer) or zero
-        float cc[16];
-        if (L.csrc) frag_load(L.csrc, L.ld_csrc, f, c0, 256, vec2_ok(L.csrc, L.ld_csrc), cc);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int col = c0 + 8 * (e >> 2) + 2 * f.a + (e & 1);
-          if (col >= nmain) r[e] = L.csrc ? cc[e] : 0.0f;
-        }
+  }
+  // ---- results to HBM
+  if (n_tma_out) {
+    mbar_wait(t.out_free, t.out_phase);
+    t.out_phase ^= 1;
+    uint8_t* o0 = t.slots_out + ((n_tma_out == 1 ? (t.out_units % kSlotsOut) : 0) * kSlotBytes);
+    uint8_t* o1 = t.slots_out + kSlotBytes;
+    if (tma_save) slot_write16(o0, rl, r);
+    if (tma_out2) slot_write16(tma_save ? o1 : o0, rl, q2);
+    fence_proxy_async_smem();
+  }
+  if (st_save && !tma_save) row_store16(L.save, L.ld_save, row, c0, nmain - c0, row_ok, r);
+  if (st_out2 && !tma_out2) row_store16(L.out2, L.ldo2, row, c0, nmain - c0, row_ok, q2);
+  if (n_tma_out || in_mask) {
+    team_sync(t.team);          // slots of this unit: inputs consumed by all 128 threads, outputs complete
+    if (t.leader) {
+      if (n_tma_out) {
+        uint8_t* o0 = t.slots_out + ((n_tma_out == 1 ? (t.out_units % kSlotsOut) : 0) * kSlotBytes);
+        uint8_t* o1 = t.slots_out + kSlotBytes;
+        if (tma_save) tma_store_2d(&p.maps[L.map[OP_SAVE]], o0, c0, tile * CH_BM);
+        if (tma_out2) tma_store_2d(&p.maps[L.map[OP_OUT2]], tma_save ? o1 : o0, c0, tile * CH_BM);
+        tma_commit();
       }
-      // two-halves layers: the half-1 MMAs of THIS layer still read K < 128 of the current A operand while half 0 is
-      // processed; its first k-chunks retire long before the first unit gets here, but the order must not rest on timing
-      if (a_free && c0 < 128) {
-        mbar_wait(a_free, phase1);
-        tcgen05_fence_after();
-        a_free = nullptr;
-      }
-      frag_write_a(tl, c0, r);
+      fifo_fill(p, t, num_tiles, tile_step);
     }
+    if (n_tma_out) { ++t.out_units; t.last_out_n = n_tma_out; }
   }
 }
 
 // FAM: 0 = bias/activation epilogues (forward chains), 1 = derivative-product epilogues (gradient sweeps), 2 = tangent
-// sweep.  One instantiation per family keeps the register pressure of each kernel low enough for ptxas to overlap
-// the sixteen independent MUFU chains of a block instead of serialising them through one register.
+// sweep.  One instantiation per family keeps the register pressure of each kernel low.
 template <int FAM>
-__global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_constant__ ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_epi = reinterpret_cast<float*>(smem + kChStages * kChStageBytes);
-  float* s_bias2 = reinterpret_cast<float*>(smem + kChStages * kChStageBytes + kChEpiBytes);   // [2][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChStages * kChStageBytes + kChEpiBytes + kChBiasBytes);
-  uint64_t* full = bars;                        // [stages]  W chunk landed
-  uint64_t* empty = bars + kChStages;           // [stages]  W chunk consumed
-  uint64_t* a_ready = bars + 2 * kChStages;     // A operand written + accumulator drained (12 epilogue warps)
-  uint64_t* acc_ready = bars + 2 * kChStages + 1;   // [2]: accumulator columns of N half 0 / half 1 complete
-  uint64_t* a_free = bars + 2 * kChStages + 3;      // half-1 MMAs are done reading K < 128 of the current A operand
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kChStages + 4);
+__global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_constant__ ChainParamsDev p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_slots = smem + kWStages * kWStageBytes;
+  float* s_bias2 = reinterpret_cast<float*>(s_slots + kSlotsBytes);   // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + kSlotsBytes + kChBiasBytes);
+  uint64_t* full = bars;                               // [kWStages]  W stage landed
+  uint64_t* empty = bars + kWStages;                   // [kWStages]  W stage consumed
+  uint64_t* a_ready = bars + 2 * kWStages;             // A operand written + accumulator drained (all epilogue warps)
+  uint64_t* acc_ready = bars + 2 * kWStages + 1;       // accumulator of the current layer complete
+  uint64_t* t_full = bars + 2 * kWStages + 2;          // [kTeams][kSlotsIn]
+  uint64_t* t_outfree = t_full + kTeams * kSlotsIn;    // [kTeams]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_outfree + kTeams);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int M = p.m_ptr ? *p.m_ptr : p.m_cap;
   if (M > p.m_cap) M = p.m_cap;
   const int num_tiles = (M + CH_BM - 1) / CH_BM;
+  const int tile_step = gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kChStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    if (smem_u32(smem) & 1023u) { printf("nero: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_ready, kChEpiWarps);
     mbar_init(acc_ready, 1);
-    mbar_init(acc_ready + 1, 1);
-    mbar_init(a_free, 1);
+    for (int i = 0; i < kTeams * kSlotsIn; ++i) mbar_init(&t_full[i], 1);
+    for (int i = 0; i < kTeams; ++i) mbar_init(&t_outfree[i], 1);
     fence_mbar_init();
   }
   if (warp == kChLoadWarp) tmem_alloc<512>(tmem_slot);
@@ -430,110 +460,102 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kChEpiWarps) {
-    // ============================== epilogue warps
-    const int lg = warp & 3, third = warp >> 2;
-    float* stg = s_epi + warp * (32 * kStagePitch);
-    const uint32_t tl = tmem_base + (uint32_t(lg * 32) << 16);
-    uint32_t acc_phase = 0, acc_phase1 = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int row0 = tile * CH_BM + lg * 32;
-      const int rows_valid = min(32, M - row0);
+    // ============================== epilogue teams
+    TeamCtx t;
+    t.team = warp >> 2; t.q = warp & 3; t.lane = lane;
+    t.leader = (t.q == 0 && lane == 0);
+    t.slots_in = s_slots + t.team * (kSlotsIn + kSlotsOut) * kSlotBytes;
+    t.slots_out = t.slots_in + kSlotsIn * kSlotBytes;
+    t.full = t_full + t.team * kSlotsIn;
+    t.out_free = t_outfree + t.team;
+    t.cons_seq = 0; t.out_phase = 0; t.out_units = 0; t.last_out_n = 2;
+    t.prod.tile = blockIdx.x; t.prod.li = -1; t.prod.u = t.team; t.prod.op = 0; t.prod.seq = 0;
+    t.prod_live = true;
+    const uint32_t tl = tmem_base + (uint32_t(t.q * 32) << 16);
+    if (t.leader) fifo_fill(p, t, num_tiles, tile_step);
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
+      const int rows_valid = min(CH_BM, M - tile * CH_BM);
+      const int rl = t.q * 32 + lane;
+      const long row = long(tile) * CH_BM + rl;
+      const bool row_ok = rl < rows_valid;
+      // TMA stores write whole boxes clipped at the tensor extent (m_cap rows): on a ragged tile with M < m_cap the rows
+      // beyond M lie inside the extent and must not be written, so that tile stores row by row
+      const bool tma_store_ok = (rows_valid == CH_BM) || (M >= p.m_cap);
       // ---- first A operand: fp32 rows from HBM -> split-bf16 in TMEM
-      {
-#if NERO_EPI_V2
-        const bool v0 = vec2_ok(p.A0, p.lda0);
-        const int nu0 = p.L[0].k_chunks * 4;      // [16 x 32] units: every column the first layer's MMAs read (zeros beyond k_valid0)
-        for (int u = third; u < nu0; u += 3) {
-          const int h = u & 1, c0 = (u >> 1) * 32;
-          const int rl = h * 16 + (lane >> 2);
-          FragPos f;
-          f.rlo = row0 + rl; f.a = lane & 3; f.plo = rl < rows_valid; f.phi = rl + 8 < rows_valid;
-          float x[16];
-          frag_load(p.A0, p.lda0, f, c0, p.k_valid0, v0, x);
-          frag_write_a(tmem_base + (uint32_t(lg * 32 + h * 16) << 16), c0, x);
+      for (int u = t.team; u < p.a0_units; u += kTeams) {
+        float x[16];
+        if (p.a0_tma) {
+          slot_read16(fifo_pop(t), rl, x);
+          team_sync(t.team);
+          if (t.leader) fifo_fill(p, t, num_tiles, tile_step);
+        } else {
+          row_load16(p.A0, p.lda0, row, u * 16, p.k_valid0 - u * 16, row_ok, x);
         }
-#else
-        const bool v0 = vec_ok(p.A0, p.lda0);
-        const int nb0 = p.L[0].k_chunks * 4;      // every column the first layer's MMAs read (zeros beyond k_valid0)
-        for (int b = third; b < nb0; b += 3) {
-          float x[16];
-          load_block16(p.A0 + size_t(row0) * p.lda0 + b * 16, p.lda0, rows_valid, p.k_valid0 - b * 16, v0, stg, lane, x);
-          write_a16(tl, b * 16, x);
-        }
-#endif
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
+        write_a16(tl, u * 16, x);
       }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
       for (int l = 0; l < p.n_layers; ++l) {
-        const ChainLayer& L = p.L[l];
-        // prefetch the aux operands of THIS layer's epilogue into L2 while the MMAs run
-        if (third == 0 && rows_valid > 0 && L.kind >= EK_DACT_SOFTPLUS) {
-          const int nm = min(L.ncol_out, L.ncol_main);
-          if (L.kind != EK_DACT_NONE) prefetch_rows_l2(L.H + size_t(row0) * L.ldh, L.ldh, rows_valid, nm, lane);
-          prefetch_rows_l2(L.addend ? L.addend + size_t(row0) * L.ldadd : nullptr, L.ldadd, rows_valid, nm, lane);
-          if (L.kind == EK_TANGENT) prefetch_rows_l2(L.V + size_t(row0) * L.ldv, L.ldv, rows_valid, nm, lane);
-        }
+        const ChainLayerDev& L = p.L[l];
         // bias of this layer -> smem buffer (l & 1): written while the MMAs run; the named barrier below orders it
-        // against the reads (two buffers + one barrier per layer make the reuse race-free, see DESIGN.md)
+        // against the reads (two buffers + one barrier per layer make the reuse race-free)
         float* sb = s_bias2 + (l & 1) * 256;
-        if (warp < 8) {
+        {
           const int i = warp * 32 + lane;
-          sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
+          if (i < 256) sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
         }
-        const bool two_halves = NERO_NSPLIT && L.n_pad > 128;
         mbar_wait(acc_ready, acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
-#if NERO_EPI_V2
-#define NERO_EPI_CALL(K) chain_epilogue_layer2<K>(L, tmem_base, lg, row0, rows_valid, third, lane, sb, two_halves ? acc_ready + 1 : nullptr, two_halves ? a_free : nullptr, acc_phase1)
-#else
-#define NERO_EPI_CALL(K) chain_epilogue_layer<K>(L, tl, row0, rows_valid, third, lane, stg, sb)
-#endif
-        if constexpr (FAM == 0) {
-          if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
-          else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
-          else NERO_EPI_CALL(EK_BIAS_GENERIC);
-        } else if constexpr (FAM == 1) {
-          if (L.kind == EK_DACT_SOFTPLUS) NERO_EPI_CALL(EK_DACT_SOFTPLUS);
-          else if (L.kind == EK_DACT_RELU) NERO_EPI_CALL(EK_DACT_RELU);
-          else NERO_EPI_CALL(EK_DACT_NONE);
-        } else {
-          NERO_EPI_CALL(EK_TANGENT);
-        }
+        for (int u = t.team; u < L.n_units; u += kTeams) {
+#define NERO_EPI_CALL(K) epi_unit<K>(p, l, t, tl, u, tile, rows_valid, tma_store_ok, sb, num_tiles, tile_step)
+          if constexpr (FAM == 0) {
+            if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
+            else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
+            else NERO_EPI_CALL(EK_BIAS_GENERIC);
+          } else if constexpr (FAM == 1) {
+            if (L.kind == EK_DACT_SOFTPLUS) NERO_EPI_CALL(EK_DACT_SOFTPLUS);
+            else if (L.kind == EK_DACT_RELU) NERO_EPI_CALL(EK_DACT_RELU);
+            else NERO_EPI_CALL(EK_DACT_NONE);
+          } else {
+            NERO_EPI_CALL(EK_TANGENT);
+          }
 #undef NERO_EPI_CALL
-        if (two_halves) acc_phase1 ^= 1;
+        }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        // the last layer of the last tile has no consumer, every other (tile, layer) hands over to the MMA warp
+        // the last layer of a tile hands over nothing: the next tile's A operand is announced after its conversion
         if (lane == 0 && l + 1 < p.n_layers) mbar_arrive(a_ready);
       }
     }
+    if (t.leader) tma_wait_all();      // outstanding TMA stores must complete before the CTA exits
   } else if (warp == kChMmaWarp) {
     // ============================== MMA issuer
     int g = 0;
     uint32_t a_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
       for (int l = 0; l < p.n_layers; ++l) {
-        const ChainLayer& L = p.L[l];
-        const int nh = (NERO_NSPLIT && L.n_pad > 128) ? 2 : 1;
+        const ChainLayerDev& L = p.L[l];
+        const int nh = L.n_pad > 128 ? 2 : 1;
         const uint32_t half_rows = uint32_t(L.n_pad) / nh;
         const uint32_t idesc = make_idesc_bf16(CH_BM, half_rows);
         const uint32_t b_plane = half_rows * 128u;
         mbar_wait(a_ready, a_phase);
         a_phase ^= 1;
         tcgen05_fence_after();
-        for (int hf = 0; hf < nh; ++hf) {
-          const uint32_t d_col = tmem_base + kAccCol + uint32_t(hf) * half_rows;
-          for (int c = 0; c < L.k_chunks; ++c, ++g) {
-            const int s = g % kChStages;
-            mbar_wait(&full[s], (g / kChStages) & 1);
+        for (int c = 0; c < L.k_chunks; ++c) {
+          for (int hf = 0; hf < nh; ++hf, ++g) {
+            const int s = g % kWStages;
+            const uint32_t d_col = tmem_base + kAccCol + uint32_t(hf) * half_rows;
+            mbar_wait(&full[s], (g / kWStages) & 1);
             tcgen05_fence_after();
             if (elect_one()) {
-              const uint32_t b_hi = smem_u32(smem + s * kChStageBytes);
+              const uint32_t b_hi = smem_u32(s_w + s * kWStageBytes);
               const uint32_t b_lo = b_hi + b_plane;
 #pragma unroll
               for (int k = 0; k < CH_BK / 16; ++k) {
@@ -544,8 +566,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
                 umma_bf16_ts(d_col, tmem_base + kAHiCol + a_col, dbh, idesc, 1);
               }
               umma_commit(&empty[s]);
-              if (nh == 2 && hf == 1 && c == min(L.k_chunks, 2) - 1) umma_commit(a_free);   // K < 128 of A no longer needed
-              if (c == L.k_chunks - 1) umma_commit(acc_ready + hf);
+              if (c == L.k_chunks - 1 && hf == nh - 1) umma_commit(acc_ready);
             }
             __syncwarp();
           }
@@ -555,22 +576,22 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   } else {
     // ============================== W loader
     int g = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
       for (int l = 0; l < p.n_layers; ++l) {
-        const ChainLayer& L = p.L[l];
-        const int nh = (NERO_NSPLIT && L.n_pad > 128) ? 2 : 1;
+        const ChainLayerDev& L = p.L[l];
+        const int nh = L.n_pad > 128 ? 2 : 1;
         const uint32_t half_rows = uint32_t(L.n_pad) / nh;
         const uint32_t plane = uint32_t(L.n_pad) * 128u, hp = half_rows * 128u;
-        for (int hf = 0; hf < nh; ++hf) {
-          for (int c = 0; c < L.k_chunks; ++c, ++g) {
-            const int s = g % kChStages;
-            mbar_wait(&empty[s], ((g / kChStages) & 1) ^ 1);
+        for (int c = 0; c < L.k_chunks; ++c) {
+          for (int hf = 0; hf < nh; ++hf, ++g) {
+            const int s = g % kWStages;
+            mbar_wait(&empty[s], ((g / kWStages) & 1) ^ 1);
             if (elect_one()) {
               // rows [hf*half_rows, +half_rows) of the chunk's hi plane and of its lo plane
               const uint8_t* src = L.wimg + size_t(c) * 2u * plane + size_t(hf) * hp;
               mbar_arrive_expect_tx(&full[s], 2u * hp);
-              bulk_copy_g2s(smem + s * kChStageBytes, src, hp, &full[s]);
-              bulk_copy_g2s(smem + s * kChStageBytes + hp, src + plane, hp, &full[s]);
+              bulk_copy_g2s(s_w + s * kWStageBytes, src, hp, &full[s]);
+              bulk_copy_g2s(s_w + s * kWStageBytes + hp, src + plane, hp, &full[s]);
             }
             __syncwarp();
           }
@@ -583,11 +604,68 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   if (warp == kChLoadWarp) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  uintptr_t ptr; int ld, rows, cols;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<uintptr_t>()(k.ptr) ^ (std::hash<long long>()((long long)k.ld << 40 ^ (long long)k.rows << 12 ^ k.cols) * 0x9E3779B97F4A7C15ull);
+  }
+};
+
+// a [rows x cols] fp32 window (leading dimension ld) as a 2-D tensor map with [128 x 16] SWIZZLE_64B boxes
+static bool tma_eligible(const float* ptr, int ld, int cols) {
+  return ptr && cols >= 8 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0;
+}
+static int make_map(CUtensorMap* out, const float* ptr, int ld, int rows, int cols) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{reinterpret_cast<uintptr_t>(ptr), ld, rows, cols};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return NERO_OK; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return NERO_ERR_CUDA;
+  const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+  const cuuint32_t box[2] = {16, CH_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  const CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    fprintf(stderr, "nero_b200: cuTensorMapEncodeTiled failed (%d) for ptr %p ld %d rows %d cols %d\n", int(rc), (const void*)ptr, ld, rows, cols);
+    return NERO_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return NERO_OK;
+}
+
 int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
-  if (p.n_layers <= 0 || p.n_layers > kMaxChainLayers || (p.lda0 & 3) || p.k_valid0 > 256) return NERO_ERR_ARG;
+  if (p.n_layers <= 0 || p.n_layers > kMaxChainLayers || (p.lda0 & 3) || p.k_valid0 > 256 || !p.A0) return NERO_ERR_ARG;
   for (int l = 0; l < p.n_layers; ++l) {
     const ChainLayer& L = p.L[l];
     if (L.n_pad % 16 || L.n_pad < 16 || L.n_pad > 256 || L.k_chunks < 1 || L.k_chunks > 4 || L.ncol_out > L.n_pad) return NERO_ERR_ARG;
+    if (L.n_pad > 128 && (L.n_pad / 2) % 16) return NERO_ERR_ARG;
     if (L.kind == EK_TANGENT && (!L.H || !L.V || !L.out2)) return NERO_ERR_ARG;
     if ((L.kind == EK_DACT_SOFTPLUS || L.kind == EK_DACT_RELU) && !L.H) return NERO_ERR_ARG;
   }
@@ -598,6 +676,48 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
     if (fam >= 0 && f != fam) return NERO_ERR_ARG;   // a chain is homogeneous: forward, gradient sweep or tangent sweep
     fam = f;
   }
+  const int tiles_cap = (p.m_cap + CH_BM - 1) / CH_BM;
+  if (tiles_cap <= 0) return NERO_OK;
+
+  static ChainParamsDev d;       // (host calls are serialised by the Python GIL; the struct is copied at launch)
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  d.A0 = p.A0; d.lda0 = p.lda0; d.k_valid0 = p.k_valid0; d.n_layers = p.n_layers; d.m_ptr = p.m_ptr; d.m_cap = p.m_cap;
+  d.a0_units = p.L[0].k_chunks * 4;           // every column the first layer's MMAs read (zeros beyond k_valid0)
+  int nmaps = 1;
+  d.a0_tma = tma_eligible(p.A0, p.lda0, p.k_valid0) ? 1 : 0;
+  if (d.a0_tma && make_map(&d.maps[0], p.A0, p.lda0, p.m_cap, p.k_valid0) != NERO_OK) return NERO_ERR_CUDA;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const ChainLayer& s = p.L[l];
+    ChainLayerDev& o = d.L[l];
+    o.wimg = s.wimg; o.bias = s.bias; o.save = s.save; o.H = s.H; o.out2 = s.out2; o.tail = s.tail; o.csrc = s.csrc;
+    o.n_pad = s.n_pad; o.k_chunks = s.k_chunks; o.n_bias = s.n_bias; o.ncol_out = s.ncol_out; o.ncol_main = s.ncol_main; o.kind = s.kind; o.act = s.act;
+    o.ld_save = s.ld_save; o.ldh = s.ldh; o.ldo2 = s.ldo2; o.ldt = s.ldt; o.ld_csrc = s.ld_csrc;
+    o.oscale = s.oscale; o.hscale = s.hscale; o.act_param = s.act_param; o.write_a = s.write_a; o.a_blocks = s.a_blocks;
+    const bool tangent = s.kind == EK_TANGENT;
+    o.aux2 = tangent ? s.V : (s.kind >= EK_DACT_SOFTPLUS ? s.addend : nullptr);
+    o.ld2 = tangent ? s.ldv : s.ldadd;
+    o.aux2_is_addend = tangent ? 0 : 1;
+    const int nblk = s.n_pad / 16;
+    const int nblk_a = s.write_a ? (s.a_blocks > nblk ? s.a_blocks : nblk) : 0;
+    o.n_units = nblk > nblk_a ? nblk : nblk_a;
+    const bool bias_kind = s.kind <= EK_BIAS_GENERIC;
+    const int nmain = bias_kind ? s.ncol_out : (s.ncol_out < s.ncol_main ? s.ncol_out : s.ncol_main);
+    o.tma = 0;
+    struct { int op; const float* ptr; int ld; int cols; bool use; } ops[OP_COUNT] = {
+        {OP_H, s.H, s.ldh, nmain, !bias_kind && s.kind != EK_DACT_NONE},
+        {OP_AUX2, o.aux2, o.ld2, nmain, !bias_kind},
+        {OP_CSRC, s.csrc, s.ld_csrc, 256, s.write_a != 0},
+        {OP_SAVE, s.save, s.ld_save, nmain, true},
+        {OP_OUT2, s.out2, s.ldo2, nmain, tangent}};
+    for (auto& q : ops) {
+      o.map[q.op] = 0;
+      if (!q.use || !tma_eligible(q.ptr, q.ld, q.cols)) continue;
+      if (make_map(&d.maps[nmaps], q.ptr, q.ld, p.m_cap, q.cols) != NERO_OK) return NERO_ERR_CUDA;
+      o.map[q.op] = nmaps++;
+      o.tma |= 1 << q.op;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(umma_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes) != cudaSuccess ||
@@ -606,12 +726,10 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
       return NERO_ERR_CUDA;
     attr_set = true;
   }
-  const int tiles_cap = (p.m_cap + CH_BM - 1) / CH_BM;
-  if (tiles_cap <= 0) return NERO_OK;
   const int grid = tiles_cap < kNumSMs ? tiles_cap : kNumSMs;
-  if (fam == 0) umma_chain_kernel<0><<<grid, kChThreads, kChSmemBytes, stream>>>(p);
-  else if (fam == 1) umma_chain_kernel<1><<<grid, kChThreads, kChSmemBytes, stream>>>(p);
-  else umma_chain_kernel<2><<<grid, kChThreads, kChSmemBytes, stream>>>(p);
+  if (fam == 0) umma_chain_kernel<0><<<grid, kChThreads, kChSmemBytes, stream>>>(d);
+  else if (fam == 1) umma_chain_kernel<1><<<grid, kChThreads, kChSmemBytes, stream>>>(d);
+  else umma_chain_kernel<2><<<grid, kChThreads, kChSmemBytes, stream>>>(d);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }
