@@ -66,6 +66,8 @@ struct ChainLayerDev {
   int tma;                     // bit o set: operand o moves through TMA (tensor map maps[map[o]])
   int map[OP_COUNT];
   int n_units;                 // 16-column units the epilogue walks (accumulator columns + next-A columns to define)
+  int n_full;                  // units completely inside the valid columns: the ones with TMA traffic
+  int in_ops, out_ops;         // operand bits loaded / stored through TMA by those units
 };
 constexpr int kMaxMaps = 1 + kMaxChainLayers * OP_COUNT;
 struct ChainParamsDev {
@@ -76,20 +78,33 @@ struct ChainParamsDev {
 };
 
 // ---------------------------------------------------------------------------------------------- configuration
+#ifndef NERO_TEAMS
+#define NERO_TEAMS 3
+#endif
+#ifndef NERO_SLOTS_IN
+#define NERO_SLOTS_IN 2
+#endif
+#ifndef NERO_SLOTS_OUT
+#define NERO_SLOTS_OUT 2
+#endif
 constexpr int CH_BM = 128, CH_BK = 64;
-constexpr int kTeams = 2;                          // epilogue teams (4 warps each, one per TMEM lane quarter)
+constexpr int kTeams = NERO_TEAMS;                 // epilogue teams (4 warps each, one per TMEM lane quarter)
 constexpr int kChEpiWarps = 4 * kTeams;
-constexpr int kChMmaWarp = kChEpiWarps, kChLoadWarp = kChEpiWarps + 1;
-constexpr int kChThreads = (kChEpiWarps + 2) * 32;
-constexpr int kWStages = 4;
-constexpr uint32_t kWStageBytes = 2 * 128 * 128;   // hi + lo planes of up to 128 weight rows x 64 K
-constexpr int kSlotsIn = 4, kSlotsOut = 2;         // per team
+constexpr int kChMmaWarp = kChEpiWarps, kChLoadWarp = kChEpiWarps + 1, kChAuxWarp = kChEpiWarps + 2, kChStoreWarp = kChEpiWarps + 3;
+constexpr int kChThreads = (kChEpiWarps + 4) * 32;
+#ifndef NERO_WSTAGES
+#define NERO_WSTAGES 4
+#endif
+constexpr int kWStages = NERO_WSTAGES;
+constexpr uint32_t kWStageBytes = 2 * 128 * 128;   // hi + lo planes of up to 128 weight rows x 64 K (one N half of a K chunk)
+constexpr int kSlotsIn = NERO_SLOTS_IN, kSlotsOut = NERO_SLOTS_OUT;         // per team
 constexpr uint32_t kSlotBytes = CH_BM * 16 * 4;    // [128 rows x 16 fp32] = 8 KB
 constexpr uint32_t kSlotsBytes = kTeams * (kSlotsIn + kSlotsOut) * kSlotBytes;
 constexpr uint32_t kChBiasBytes = 2 * 256 * 4;
 constexpr uint32_t kChBarBytes = 512;
 constexpr uint32_t kChSmemBytes = kWStages * kWStageBytes + kSlotsBytes + kChBiasBytes + kChBarBytes;
 static_assert(kChSmemBytes <= 232448, "shared memory budget");
+static_assert((2 * kWStages + 2 + 2 * kTeams * (kSlotsIn + kSlotsOut)) * 8 + 8 <= kChBarBytes, "barrier area");
 constexpr uint32_t kAccCol = 0, kAHiCol = 256, kALoCol = 384;
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -126,7 +141,6 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 template <int N>
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 2) : "memory"); }
 
 // write 16 fp32 values of this lane's row (columns c0..c0+15 of the next A operand) as packed split-bf16 into TMEM
 __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const float* y) {
@@ -138,25 +152,24 @@ __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const
 }
 
 // one row (this thread's) of a [128 x 16] fp32 slot in the SWIZZLE_64B layout: 64-byte rows, the 16-byte chunk index is
-// XORed with bits 1..2 of the row (the pattern cuTensorMapEncodeTiled(..., SWIZZLE_64B) uses; slots are 1024-B aligned)
-__device__ __forceinline__ void slot_read16(const uint8_t* slot, int row, float* x) {
-  const uint8_t* base = slot + row * 64;
-  const int sw = (row >> 1) & 3;
+// XORed with bits 1..2 of the row (the pattern cuTensorMapEncodeTiled(..., SWIZZLE_64B) uses; slots are 1024-B aligned).
+// `rowoff` = row*64, `sw` = ((row >> 1) & 3) << 4 are per-thread constants.
+__device__ __forceinline__ void slot_read16(const uint8_t* slot, uint32_t rowoff, uint32_t sw, float* x) {
+  const uint8_t* base = slot + rowoff;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float4 v = *reinterpret_cast<const float4*>(base + ((j ^ sw) << 4));
+    const float4 v = *reinterpret_cast<const float4*>(base + ((j << 4) ^ sw));
     x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
   }
 }
-__device__ __forceinline__ void slot_write16(uint8_t* slot, int row, const float* x) {
-  uint8_t* base = slot + row * 64;
-  const int sw = (row >> 1) & 3;
+__device__ __forceinline__ void slot_write16(uint8_t* slot, uint32_t rowoff, uint32_t sw, const float* x) {
+  uint8_t* base = slot + rowoff;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<float4*>(base + ((j ^ sw) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    *reinterpret_cast<float4*>(base + ((j << 4) ^ sw)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
 }
 // direct (non-TMA) access of this thread's row: narrow / unaligned operands and the ragged last tile
-__device__ __forceinline__ void row_load16(const float* __restrict__ g, int ld, long row, int c0, int ncols, bool row_ok, float* x) {
+__device__ __noinline__ void row_load16(const float* __restrict__ g, int ld, long row, int c0, int ncols, bool row_ok, float* x) {
   const float* p = g + row * ld + c0;
   const bool vec = row_ok && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 #pragma unroll
@@ -170,7 +183,7 @@ __device__ __forceinline__ void row_load16(const float* __restrict__ g, int ld, 
     }
   }
 }
-__device__ __forceinline__ void row_store16(float* __restrict__ g, int ld, long row, int c0, int ncols, bool row_ok, const float* x) {
+__device__ __noinline__ void row_store16(float* __restrict__ g, int ld, long row, int c0, int ncols, bool row_ok, const float* x) {
   if (!row_ok) return;
   float* p = g + row * ld + c0;
   const bool vec = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
@@ -187,95 +200,65 @@ __device__ __forceinline__ void row_store16(float* __restrict__ g, int ld, long 
 }
 
 // ---------------------------------------------------------------------------------------------- unit bookkeeping
-// Which TMA loads unit u of layer record `li` needs (li = -1: the tile's first A operand).  The leader (producer side)
-// and every thread (consumer side) of a team evaluate the same function, so the FIFO order is implied.
-__device__ __forceinline__ int layer_nmain(const ChainLayerDev& L) {
-  return (L.kind <= EK_BIAS_GENERIC) ? L.ncol_out : min(L.ncol_out, L.ncol_main);
+// TMA traffic follows ONE regular pattern per layer, so that the service lanes (aux loader / store warp) and the epilogue
+// threads agree on the FIFO order without exchanging anything: the units that lie completely inside the valid columns
+// (u < n_full = nmain / 16) load the operands in `in_ops` (H, then aux2) and store the results in `out_ops` (save, then
+// out2) through TMA, team t owning units t, t + kTeams, ...; everything else (the unit that straddles the last valid
+// column -- TMA bounds the innermost dimension in 16-byte granules: a box clipped at column 217 still wrote 217..219 --,
+// the skip-concat source, narrow or unaligned operands, the rows of a ragged last tile) is accessed row by row.
+__device__ __forceinline__ uint32_t unit_in_mask(const ChainLayerDev& L, int u) { return u < L.n_full ? uint32_t(L.in_ops) : 0u; }
+__device__ __forceinline__ uint32_t unit_out_mask(const ChainLayerDev& L, int u, bool tile_tma_ok) {
+  return (tile_tma_ok && u < L.n_full) ? uint32_t(L.out_ops) : 0u;
 }
-__device__ __forceinline__ uint32_t unit_in_mask(const ChainParamsDev& p, int li, int u) {
-  if (li < 0) return p.a0_tma ? 1u : 0u;
-  const ChainLayerDev& L = p.L[li];
-  const int c0 = u * 16, nblk = L.n_pad >> 4, nmain = layer_nmain(L);
-  uint32_t m = 0;
-  if (u < nblk && c0 < L.ncol_out && c0 < nmain) {
-    if (L.kind >= EK_DACT_SOFTPLUS && L.kind != EK_DACT_NONE && L.H) m |= 1u << OP_H;
-    if (L.aux2) m |= 1u << OP_AUX2;
-  }
-  if (L.write_a && L.csrc && c0 + 16 > nmain) m |= 1u << OP_CSRC;
-  return m & uint32_t(L.tma);
-}
-__device__ __forceinline__ int units_of(const ChainParamsDev& p, int li) { return li < 0 ? p.a0_units : p.L[li].n_units; }
-
-// FIFO position of a team: (tile, layer record, unit, operand)
-struct FifoCursor {
-  int tile, li, u, op;
-  uint32_t seq;       // loads issued / consumed so far
-};
-// advance `c` to the next TMA load at or after its position; returns false when the tile loop is exhausted
-__device__ __forceinline__ bool cursor_seek(const ChainParamsDev& p, FifoCursor& c, int team, int num_tiles, int tile_step) {
-  while (c.tile < num_tiles) {
-    while (c.li < p.n_layers) {
-      const int nu = units_of(p, c.li);
-      while (c.u < nu) {
-        const uint32_t m = unit_in_mask(p, c.li, c.u);
-        while (c.op < 3) {
-          if (m & (1u << c.op)) return true;
-          ++c.op;
-        }
-        c.op = 0;
-        c.u += kTeams;
-      }
-      ++c.li;
-      c.u = team;
-    }
-    c.tile += tile_step;
-    c.li = -1;
-    c.u = team;
-  }
-  return false;
+__device__ __forceinline__ bool tile_tma_store_ok(const ChainParamsDev& p, int tile, int M) {
+  // TMA stores write whole boxes clipped at the tensor extent (m_cap rows): on a ragged tile with M < m_cap the rows
+  // beyond M lie inside the extent and must not be written, so that tile stores row by row
+  return (M - tile * CH_BM >= CH_BM) || (M >= p.m_cap);
 }
 
+// per-thread view of its team's FIFOs
 struct TeamCtx {
   uint8_t* slots_in;        // kSlotsIn x 8 KB
   uint8_t* slots_out;       // kSlotsOut x 8 KB
-  uint64_t* full;           // [kSlotsIn]
-  uint64_t* out_free;       // leader -> team: the staging slots of the coming unit have been read by their TMA stores
-  int team, q, lane;
-  bool leader;
-  uint32_t cons_seq;        // loads consumed so far (all threads)
-  uint32_t out_phase;       // parity of out_free
-  uint32_t out_units;       // units with TMA stores so far
-  int last_out_n;           // number of TMA stores of the previous such unit
-  FifoCursor prod;          // leader only
-  bool prod_live;
+  uint64_t* in_full;        // [kSlotsIn]   TMA load landed                     (aux loader -> team)
+  uint64_t* in_empty;       // [kSlotsIn]   all four warps have read the slot   (team -> aux loader)
+  uint64_t* out_full;       // [kSlotsOut]  all four warps have written         (team -> store warp)
+  uint64_t* out_empty;      // [kSlotsOut]  the TMA store has read the slot     (store warp -> team)
+  int q, lane;
+  uint32_t rowoff, sw;      // this thread's row offset / swizzle term inside a slot
+  uint32_t in_seq, out_seq; // entries consumed / produced so far
 };
-
-// leader: issue loads until the FIFO holds kSlotsIn entries beyond `cons_seq`
-__device__ __forceinline__ void fifo_fill(const ChainParamsDev& p, TeamCtx& t, int num_tiles, int tile_step) {
-  while (t.prod_live && t.prod.seq < t.cons_seq + kSlotsIn) {
-    if (!cursor_seek(p, t.prod, t.team, num_tiles, tile_step)) { t.prod_live = false; break; }
-    const int s = t.prod.seq % kSlotsIn;
-    const CUtensorMap* map = t.prod.li < 0 ? &p.maps[0] : &p.maps[p.L[t.prod.li].map[t.prod.op]];
-    mbar_arrive_expect_tx(&t.full[s], kSlotBytes);
-    tma_load_2d(t.slots_in + s * kSlotBytes, map, t.prod.u * 16, t.prod.tile * CH_BM, &t.full[s]);
-    ++t.prod.seq;
-    ++t.prod.op;
-  }
-}
-// all threads: wait for the next FIFO entry and return its slot
-__device__ __forceinline__ const uint8_t* fifo_pop(TeamCtx& t) {
-  const uint32_t s = t.cons_seq % kSlotsIn;
-  mbar_wait(&t.full[s], (t.cons_seq / kSlotsIn) & 1);
-  ++t.cons_seq;
+__device__ __forceinline__ const uint8_t* in_wait(TeamCtx& t) {
+  const uint32_t s = t.in_seq % kSlotsIn;
+  mbar_wait(&t.in_full[s], (t.in_seq / kSlotsIn) & 1);
   return t.slots_in + s * kSlotBytes;
+}
+// release the oldest input slot: call after the values read from it have been USED (so the reads have completed)
+__device__ __forceinline__ void in_release(TeamCtx& t) {
+  __syncwarp();
+  if (t.lane == 0) mbar_arrive(&t.in_empty[t.in_seq % kSlotsIn]);
+  ++t.in_seq;
+}
+__device__ __forceinline__ uint8_t* out_acquire(TeamCtx& t) {
+  const uint32_t s = t.out_seq % kSlotsOut;
+  mbar_wait(&t.out_empty[s], ((t.out_seq / kSlotsOut) & 1) ^ 1);
+  return t.slots_out + s * kSlotBytes;
+}
+__device__ __forceinline__ void out_publish(TeamCtx& t) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (t.lane == 0) mbar_arrive(&t.out_full[t.out_seq % kSlotsOut]);
+  ++t.out_seq;
 }
 
 // ---------------------------------------------------------------------------------------------- epilogue of one unit
-template <int KIND>
-__device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx& t, uint32_t tl, int u, int tile,
-                                         int rows_valid, bool tma_store_ok, const float* s_bias, int num_tiles, int tile_step) {
-  const ChainLayerDev& L = p.L[l];
+// FAST: the unit lies completely inside the valid columns, every operand it touches moves through TMA and the tile may be
+// stored by TMA -- the common case; all run-time conditionals of the general unit fold away.
+template <int KIND, bool FAST>
+__device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx& t, uint32_t tl, int u, int tile, int rows_valid,
+                                         bool tile_tma_ok, const float* s_bias) {
   constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
+  const ChainLayerDev& L = p.L[l];
   const int c0 = u * 16;
   const int nblk = L.n_pad >> 4;
   const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
@@ -283,24 +266,14 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
   const int rl = t.q * 32 + t.lane;                 // row of this thread inside the tile
   const long row = long(tile) * CH_BM + rl;
   const bool row_ok = rl < rows_valid;
-  const uint32_t in_mask = unit_in_mask(p, l, u);
-  const bool computed = u < nblk && c0 < L.ncol_out;
-  const bool has_main = computed && c0 < nmain;
+  const uint32_t in_mask = FAST ? 0u : unit_in_mask(L, u);
+  const uint32_t out_mask = FAST ? 0u : unit_out_mask(L, u, tile_tma_ok);
+  const bool computed = FAST || (u < nblk && c0 < L.ncol_out);
+  const bool has_main = FAST || (computed && c0 < nmain);
   const bool st_save = has_main && L.save != nullptr;
   const bool st_out2 = (KIND == EK_TANGENT) && has_main;
-  const bool tma_save = st_save && (L.tma & (1 << OP_SAVE)) && tma_store_ok;
-  const bool tma_out2 = st_out2 && (L.tma & (1 << OP_OUT2)) && tma_store_ok;
-  const int n_tma_out = int(tma_save) + int(tma_out2);
-  // the staging slots this unit writes must have been read by the TMA stores of earlier units: the leader waits
-  // (bulk-group read completion) and signals the team
-  if (n_tma_out) {
-    if (t.leader) {
-      // single-output units alternate between the two slots (one earlier store may still be reading the other slot);
-      // a unit that fills both slots, or follows one that did, needs every earlier store read
-      if (n_tma_out == 1 && t.last_out_n == 1) tma_wait_read<kSlotsOut - 1>(); else tma_wait_read<0>();
-      mbar_arrive(t.out_free);
-    }
-  }
+  const bool tma_save = FAST ? st_save : (out_mask >> OP_SAVE) & 1;
+  const bool tma_out2 = FAST ? st_out2 : (out_mask >> OP_OUT2) & 1;
   float r[16];
   float q2[16];
   if (computed) {
@@ -324,11 +297,12 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
       }
     } else {
       float s[16];
+      bool rel_h = false;
       if constexpr (KIND == EK_DACT_NONE) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) s[j] = 1.0f;
       } else {
-        if (in_mask & (1u << OP_H)) slot_read16(fifo_pop(t), rl, s);
+        if (FAST || (in_mask & (1u << OP_H))) { slot_read16(in_wait(t), t.rowoff, t.sw, s); rel_h = true; }
         else if (has_main) row_load16(L.H, L.ldh, row, c0, nmain - c0, row_ok, s);
         else {
 #pragma unroll
@@ -345,9 +319,11 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
           for (int j = 0; j < 16; ++j) s[j] = 0.0f;
         }
       }
+      if (rel_h) in_release(t);
       float a2[16];
       const bool has2 = has_main && L.aux2 != nullptr;
-      if (in_mask & (1u << OP_AUX2)) slot_read16(fifo_pop(t), rl, a2);
+      bool rel_2 = false;
+      if (FAST ? has2 : bool(in_mask & (1u << OP_AUX2))) { slot_read16(in_wait(t), t.rowoff, t.sw, a2); rel_2 = true; }
       else if (has2) row_load16(L.aux2, L.ld2, row, c0, nmain - c0, row_ok, a2);
       tmem_ld_wait();
 #pragma unroll
@@ -367,7 +343,8 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
           for (int j = 0; j < 16; ++j) r[j] += a2[j];
         }
       }
-      if (L.tail && c0 + 16 > L.ncol_main && row_ok) {
+      if (rel_2) in_release(t);
+      if (!FAST && L.tail && c0 + 16 > L.ncol_main && row_ok) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = c0 + j;
@@ -380,11 +357,10 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
     for (int j = 0; j < 16; ++j) r[j] = 0.0f;
   }
   // ---- next A operand
-  if (u < nblk_a) {
-    if (c0 + 16 > nmain) {     // columns >= nmain: the skip-concat source or zero
+  if (FAST ? (L.write_a != 0) : (u < nblk_a)) {
+    if (!FAST && c0 + 16 > nmain) {     // columns >= nmain: the skip-concat source or zero
       float cc[16];
-      if (in_mask & (1u << OP_CSRC)) slot_read16(fifo_pop(t), rl, cc);
-      else if (L.csrc) row_load16(L.csrc, L.ld_csrc, row, c0, 256 - c0, row_ok, cc);
+      if (L.csrc) row_load16(L.csrc, L.ld_csrc, row, c0, 256 - c0, row_ok, cc);
       float a[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = (c0 + j >= nmain) ? (L.csrc ? cc[j] : 0.0f) : r[j];
@@ -394,31 +370,33 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
     }
   }
   // ---- results to HBM
-  if (n_tma_out) {
-    mbar_wait(t.out_free, t.out_phase);
-    t.out_phase ^= 1;
-    uint8_t* o0 = t.slots_out + ((n_tma_out == 1 ? (t.out_units % kSlotsOut) : 0) * kSlotBytes);
-    uint8_t* o1 = t.slots_out + kSlotBytes;
-    if (tma_save) slot_write16(o0, rl, r);
-    if (tma_out2) slot_write16(tma_save ? o1 : o0, rl, q2);
-    fence_proxy_async_smem();
+  if (tma_save) { slot_write16(out_acquire(t), t.rowoff, t.sw, r); out_publish(t); }
+  else if (st_save) row_store16(L.save, L.ld_save, row, c0, nmain - c0, row_ok, r);
+  if constexpr (KIND == EK_TANGENT) {
+    if (tma_out2) { slot_write16(out_acquire(t), t.rowoff, t.sw, q2); out_publish(t); }
+    else if (st_out2) row_store16(L.out2, L.ldo2, row, c0, nmain - c0, row_ok, q2);
   }
-  if (st_save && !tma_save) row_store16(L.save, L.ld_save, row, c0, nmain - c0, row_ok, r);
-  if (st_out2 && !tma_out2) row_store16(L.out2, L.ldo2, row, c0, nmain - c0, row_ok, q2);
-  if (n_tma_out || in_mask) {
-    team_sync(t.team);          // slots of this unit: inputs consumed by all 128 threads, outputs complete
-    if (t.leader) {
-      if (n_tma_out) {
-        uint8_t* o0 = t.slots_out + ((n_tma_out == 1 ? (t.out_units % kSlotsOut) : 0) * kSlotBytes);
-        uint8_t* o1 = t.slots_out + kSlotBytes;
-        if (tma_save) tma_store_2d(&p.maps[L.map[OP_SAVE]], o0, c0, tile * CH_BM);
-        if (tma_out2) tma_store_2d(&p.maps[L.map[OP_OUT2]], tma_save ? o1 : o0, c0, tile * CH_BM);
-        tma_commit();
-      }
-      fifo_fill(p, t, num_tiles, tile_step);
-    }
-    if (n_tma_out) { ++t.out_units; t.last_out_n = n_tma_out; }
+}
+
+// all units of one layer for this thread's team
+template <int KIND>
+__device__ __forceinline__ void epi_layer(const ChainParamsDev& p, int l, TeamCtx& t, int team, uint32_t tl, int tile, int rows_valid,
+                                          bool tile_tma_ok, const float* s_bias) {
+  constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
+  const ChainLayerDev& L = p.L[l];
+  const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
+  // units [0, n_fast) take the fast path: completely inside the valid columns, every operand they touch through TMA
+  bool fast_ok = tile_tma_ok && rows_valid == CH_BM;
+  if (L.save && !(L.out_ops & (1 << OP_SAVE))) fast_ok = false;
+  if (!kBias) {
+    if (KIND != EK_DACT_NONE && !(L.in_ops & (1 << OP_H))) fast_ok = false;
+    if (L.aux2 && !(L.in_ops & (1 << OP_AUX2))) fast_ok = false;
   }
+  if (KIND == EK_TANGENT && !(L.out_ops & (1 << OP_OUT2))) fast_ok = false;
+  const int n_fast = fast_ok ? L.n_full : 0;
+  int u = team;
+  for (; u < n_fast; u += kTeams) epi_unit<KIND, true>(p, l, t, tl, u, tile, rows_valid, tile_tma_ok, s_bias);
+  for (; u < L.n_units; u += kTeams) epi_unit<KIND, false>(p, l, t, tl, u, tile, rows_valid, tile_tma_ok, s_bias);
 }
 
 // FAM: 0 = bias/activation epilogues (forward chains), 1 = derivative-product epilogues (gradient sweeps), 2 = tangent
@@ -434,9 +412,11 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   uint64_t* empty = bars + kWStages;                   // [kWStages]  W stage consumed
   uint64_t* a_ready = bars + 2 * kWStages;             // A operand written + accumulator drained (all epilogue warps)
   uint64_t* acc_ready = bars + 2 * kWStages + 1;       // accumulator of the current layer complete
-  uint64_t* t_full = bars + 2 * kWStages + 2;          // [kTeams][kSlotsIn]
-  uint64_t* t_outfree = t_full + kTeams * kSlotsIn;    // [kTeams]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_outfree + kTeams);
+  uint64_t* b_in_full = bars + 2 * kWStages + 2;       // [kTeams][kSlotsIn]
+  uint64_t* b_in_empty = b_in_full + kTeams * kSlotsIn;
+  uint64_t* b_out_full = b_in_empty + kTeams * kSlotsIn;   // [kTeams][kSlotsOut]
+  uint64_t* b_out_empty = b_out_full + kTeams * kSlotsOut;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_out_empty + kTeams * kSlotsOut);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int M = p.m_ptr ? *p.m_ptr : p.m_cap;
@@ -449,8 +429,8 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_ready, kChEpiWarps);
     mbar_init(acc_ready, 1);
-    for (int i = 0; i < kTeams * kSlotsIn; ++i) mbar_init(&t_full[i], 1);
-    for (int i = 0; i < kTeams; ++i) mbar_init(&t_outfree[i], 1);
+    for (int i = 0; i < kTeams * kSlotsIn; ++i) { mbar_init(&b_in_full[i], 1); mbar_init(&b_in_empty[i], 4); }
+    for (int i = 0; i < kTeams * kSlotsOut; ++i) { mbar_init(&b_out_full[i], 4); mbar_init(&b_out_empty[i], 1); }
     fence_mbar_init();
   }
   if (warp == kChLoadWarp) tmem_alloc<512>(tmem_slot);
@@ -461,38 +441,37 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
 
   if (warp < kChEpiWarps) {
     // ============================== epilogue teams
+    const int team = warp >> 2;
     TeamCtx t;
-    t.team = warp >> 2; t.q = warp & 3; t.lane = lane;
-    t.leader = (t.q == 0 && lane == 0);
-    t.slots_in = s_slots + t.team * (kSlotsIn + kSlotsOut) * kSlotBytes;
+    t.q = warp & 3; t.lane = lane;
+    t.slots_in = s_slots + team * (kSlotsIn + kSlotsOut) * kSlotBytes;
     t.slots_out = t.slots_in + kSlotsIn * kSlotBytes;
-    t.full = t_full + t.team * kSlotsIn;
-    t.out_free = t_outfree + t.team;
-    t.cons_seq = 0; t.out_phase = 0; t.out_units = 0; t.last_out_n = 2;
-    t.prod.tile = blockIdx.x; t.prod.li = -1; t.prod.u = t.team; t.prod.op = 0; t.prod.seq = 0;
-    t.prod_live = true;
+    t.in_full = b_in_full + team * kSlotsIn;
+    t.in_empty = b_in_empty + team * kSlotsIn;
+    t.out_full = b_out_full + team * kSlotsOut;
+    t.out_empty = b_out_empty + team * kSlotsOut;
+    t.in_seq = 0; t.out_seq = 0;
+    const int rl = t.q * 32 + lane;
+    t.rowoff = uint32_t(rl) * 64u;
+    t.sw = uint32_t((rl >> 1) & 3) << 4;
     const uint32_t tl = tmem_base + (uint32_t(t.q * 32) << 16);
-    if (t.leader) fifo_fill(p, t, num_tiles, tile_step);
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
       const int rows_valid = min(CH_BM, M - tile * CH_BM);
-      const int rl = t.q * 32 + lane;
       const long row = long(tile) * CH_BM + rl;
       const bool row_ok = rl < rows_valid;
-      // TMA stores write whole boxes clipped at the tensor extent (m_cap rows): on a ragged tile with M < m_cap the rows
-      // beyond M lie inside the extent and must not be written, so that tile stores row by row
-      const bool tma_store_ok = (rows_valid == CH_BM) || (M >= p.m_cap);
+      const bool tile_tma_ok = tile_tma_store_ok(p, tile, M);
       // ---- first A operand: fp32 rows from HBM -> split-bf16 in TMEM
-      for (int u = t.team; u < p.a0_units; u += kTeams) {
+      for (int u = team; u < p.a0_units; u += kTeams) {
         float x[16];
         if (p.a0_tma) {
-          slot_read16(fifo_pop(t), rl, x);
-          team_sync(t.team);
-          if (t.leader) fifo_fill(p, t, num_tiles, tile_step);
+          slot_read16(in_wait(t), t.rowoff, t.sw, x);
+          write_a16(tl, u * 16, x);
+          in_release(t);
         } else {
           row_load16(p.A0, p.lda0, row, u * 16, p.k_valid0 - u * 16, row_ok, x);
+          write_a16(tl, u * 16, x);
         }
-        write_a16(tl, u * 16, x);
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -511,21 +490,19 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         acc_phase ^= 1;
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
-        for (int u = t.team; u < L.n_units; u += kTeams) {
-#define NERO_EPI_CALL(K) epi_unit<K>(p, l, t, tl, u, tile, rows_valid, tma_store_ok, sb, num_tiles, tile_step)
-          if constexpr (FAM == 0) {
-            if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
-            else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
-            else NERO_EPI_CALL(EK_BIAS_GENERIC);
-          } else if constexpr (FAM == 1) {
-            if (L.kind == EK_DACT_SOFTPLUS) NERO_EPI_CALL(EK_DACT_SOFTPLUS);
-            else if (L.kind == EK_DACT_RELU) NERO_EPI_CALL(EK_DACT_RELU);
-            else NERO_EPI_CALL(EK_DACT_NONE);
-          } else {
-            NERO_EPI_CALL(EK_TANGENT);
-          }
-#undef NERO_EPI_CALL
+#define NERO_EPI_CALL(K) epi_layer<K>(p, l, t, team, tl, tile, rows_valid, tile_tma_ok, sb)
+        if constexpr (FAM == 0) {
+          if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
+          else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
+          else NERO_EPI_CALL(EK_BIAS_GENERIC);
+        } else if constexpr (FAM == 1) {
+          if (L.kind == EK_DACT_SOFTPLUS) NERO_EPI_CALL(EK_DACT_SOFTPLUS);
+          else if (L.kind == EK_DACT_RELU) NERO_EPI_CALL(EK_DACT_RELU);
+          else NERO_EPI_CALL(EK_DACT_NONE);
+        } else {
+          NERO_EPI_CALL(EK_TANGENT);
         }
+#undef NERO_EPI_CALL
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -533,7 +510,6 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         if (lane == 0 && l + 1 < p.n_layers) mbar_arrive(a_ready);
       }
     }
-    if (t.leader) tma_wait_all();      // outstanding TMA stores must complete before the CTA exits
   } else if (warp == kChMmaWarp) {
     // ============================== MMA issuer
     int g = 0;
@@ -573,7 +549,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         }
       }
     }
-  } else {
+  } else if (warp == kChLoadWarp) {
     // ============================== W loader
     int g = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
@@ -597,6 +573,72 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           }
         }
       }
+    }
+  } else if (warp == kChAuxWarp) {
+    // ============================== aux loader: lane t fills the input FIFO of team t, as far ahead as slots are free
+    if (lane < kTeams) {
+      const int tm = lane;
+      uint64_t* fb = b_in_full + tm * kSlotsIn;
+      uint64_t* eb = b_in_empty + tm * kSlotsIn;
+      uint8_t* slots = s_slots + tm * (kSlotsIn + kSlotsOut) * kSlotBytes;
+      uint32_t seq = 0;
+      auto issue = [&](const CUtensorMap* map, int c0, int r0) {
+        const uint32_t s_ = seq % kSlotsIn;
+        mbar_wait(&eb[s_], ((seq / kSlotsIn) & 1) ^ 1);          // the team has read the previous contents
+        mbar_arrive_expect_tx(&fb[s_], kSlotBytes);
+        tma_load_2d(slots + s_ * kSlotBytes, map, c0, r0, &fb[s_]);
+        ++seq;
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
+        const int r0 = tile * CH_BM;
+        if (p.a0_tma)
+          for (int u = tm; u < p.a0_units; u += kTeams) issue(&p.maps[0], u * 16, r0);
+        for (int l = 0; l < p.n_layers; ++l) {
+          const ChainLayerDev& L = p.L[l];
+          if (!L.in_ops) continue;
+          const CUtensorMap* mh = (L.in_ops & (1 << OP_H)) ? &p.maps[L.map[OP_H]] : nullptr;
+          const CUtensorMap* m2 = (L.in_ops & (1 << OP_AUX2)) ? &p.maps[L.map[OP_AUX2]] : nullptr;
+          for (int u = tm; u < L.n_full; u += kTeams) {
+            if (mh) issue(mh, u * 16, r0);
+            if (m2) issue(m2, u * 16, r0);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================== store warp: lane t drains the output FIFO of team t with TMA stores
+    if (lane < kTeams) {
+      const int tm = lane;
+      uint64_t* fb = b_out_full + tm * kSlotsOut;
+      uint64_t* eb = b_out_empty + tm * kSlotsOut;
+      uint8_t* slots = s_slots + (tm * (kSlotsIn + kSlotsOut) + kSlotsIn) * kSlotBytes;
+      uint32_t seq = 0;
+      auto issue = [&](const CUtensorMap* map, int c0, int r0) {
+        const uint32_t s_ = seq % kSlotsOut;
+        mbar_wait(&fb[s_], (seq / kSlotsOut) & 1);                 // all four warps of the team have written their rows
+        tma_store_2d(map, slots + s_ * kSlotBytes, c0, r0);
+        tma_commit();
+        if (seq > 0) {                                             // the previous store has read its slot: hand it back
+          tma_wait_read<1>();
+          mbar_arrive(&eb[(seq - 1) % kSlotsOut]);
+        }
+        ++seq;
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
+        if (!tile_tma_store_ok(p, tile, M)) continue;
+        const int r0 = tile * CH_BM;
+        for (int l = 0; l < p.n_layers; ++l) {
+          const ChainLayerDev& L = p.L[l];
+          if (!L.out_ops) continue;
+          const CUtensorMap* ms = (L.out_ops & (1 << OP_SAVE)) ? &p.maps[L.map[OP_SAVE]] : nullptr;
+          const CUtensorMap* m2 = (L.out_ops & (1 << OP_OUT2)) ? &p.maps[L.map[OP_OUT2]] : nullptr;
+          for (int u = tm; u < L.n_full; u += kTeams) {
+            if (ms) issue(ms, u * 16, r0);
+            if (m2) issue(m2, u * 16, r0);
+          }
+        }
+      }
+      tma_wait_all();      // outstanding TMA stores must complete before the CTA exits
     }
   }
   tcgen05_fence_before();
@@ -707,7 +749,7 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
     struct { int op; const float* ptr; int ld; int cols; bool use; } ops[OP_COUNT] = {
         {OP_H, s.H, s.ldh, nmain, !bias_kind && s.kind != EK_DACT_NONE},
         {OP_AUX2, o.aux2, o.ld2, nmain, !bias_kind},
-        {OP_CSRC, s.csrc, s.ld_csrc, 256, s.write_a != 0},
+        {OP_CSRC, s.csrc, s.ld_csrc, 256, false},        // the skip-concat source is read row by row
         {OP_SAVE, s.save, s.ld_save, nmain, true},
         {OP_OUT2, s.out2, s.ldo2, nmain, tangent}};
     for (auto& q : ops) {
@@ -717,6 +759,10 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
       o.map[q.op] = nmaps++;
       o.tma |= 1 << q.op;
     }
+    const int ncomp = nmain < s.ncol_out ? nmain : s.ncol_out;
+    o.n_full = ncomp / 16;
+    o.in_ops = o.n_full ? (o.tma & ((1 << OP_H) | (1 << OP_AUX2))) : 0;
+    o.out_ops = o.n_full ? (o.tma & ((1 << OP_SAVE) | (1 << OP_OUT2))) : 0;
   }
   static bool attr_set = false;
   if (!attr_set) {
