@@ -104,7 +104,7 @@ constexpr uint32_t kChBiasBytes = 2 * 256 * 4;
 constexpr uint32_t kChBarBytes = 512;
 constexpr uint32_t kChSmemBytes = kWStages * kWStageBytes + kSlotsBytes + kChBiasBytes + kChBarBytes;
 static_assert(kChSmemBytes <= 232448, "shared memory budget");
-static_assert((2 * kWStages + 2 + 2 * kTeams * (kSlotsIn + kSlotsOut)) * 8 + 8 <= kChBarBytes, "barrier area");
+static_assert((2 * kWStages + 5 + 2 * kTeams * (kSlotsIn + kSlotsOut)) * 8 + 8 <= kChBarBytes, "barrier area");
 constexpr uint32_t kAccCol = 0, kAHiCol = 256, kALoCol = 384;
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -206,7 +206,9 @@ __device__ __noinline__ void row_store16(float* __restrict__ g, int ld, long row
 // out2) through TMA, team t owning units t, t + kTeams, ...; everything else (the unit that straddles the last valid
 // column -- TMA bounds the innermost dimension in 16-byte granules: a box clipped at column 217 still wrote 217..219 --,
 // the skip-concat source, narrow or unaligned operands, the rows of a ragged last tile) is accessed row by row.
-__device__ __forceinline__ uint32_t unit_in_mask(const ChainLayerDev& L, int u) { return u < L.n_full ? uint32_t(L.in_ops) : 0u; }
+__device__ __forceinline__ uint32_t unit_in_mask(const ChainLayerDev& L, int u) {
+  return u < L.n_full ? uint32_t(L.in_ops) & ~(1u << OP_CSRC) : uint32_t(L.in_ops) & (1u << OP_CSRC);
+}
 __device__ __forceinline__ uint32_t unit_out_mask(const ChainLayerDev& L, int u, bool tile_tma_ok) {
   return (tile_tma_ok && u < L.n_full) ? uint32_t(L.out_ops) : 0u;
 }
@@ -254,9 +256,9 @@ __device__ __forceinline__ void out_publish(TeamCtx& t) {
 // ---------------------------------------------------------------------------------------------- epilogue of one unit
 // FAST: the unit lies completely inside the valid columns, every operand it touches moves through TMA and the tile may be
 // stored by TMA -- the common case; all run-time conditionals of the general unit fold away.
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, typename PreWrite>
 __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx& t, uint32_t tl, int u, int tile, int rows_valid,
-                                         bool tile_tma_ok, const float* s_bias) {
+                                         bool tile_tma_ok, const float* s_bias, PreWrite&& before_a_write) {
   constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
   const ChainLayerDev& L = p.L[l];
   const int c0 = u * 16;
@@ -358,12 +360,16 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
   }
   // ---- next A operand
   if (FAST ? (L.write_a != 0) : (u < nblk_a)) {
+    before_a_write(u);
     if (!FAST && c0 + 16 > nmain) {     // columns >= nmain: the skip-concat source or zero
       float cc[16];
-      if (L.csrc) row_load16(L.csrc, L.ld_csrc, row, c0, 256 - c0, row_ok, cc);
+      const bool tma_c = (in_mask >> OP_CSRC) & 1;
+      if (tma_c) slot_read16(in_wait(t), t.rowoff, t.sw, cc);
+      else if (L.csrc) row_load16(L.csrc, L.ld_csrc, row, c0, 256 - c0, row_ok, cc);
       float a[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) a[j] = (c0 + j >= nmain) ? (L.csrc ? cc[j] : 0.0f) : r[j];
+      if (tma_c) in_release(t);
       write_a16(tl, c0, a);
     } else {
       write_a16(tl, c0, r);
@@ -379,9 +385,9 @@ __device__ __forceinline__ void epi_unit(const ChainParamsDev& p, int l, TeamCtx
 }
 
 // all units of one layer for this thread's team
-template <int KIND>
-__device__ __forceinline__ void epi_layer(const ChainParamsDev& p, int l, TeamCtx& t, int team, uint32_t tl, int tile, int rows_valid,
-                                          bool tile_tma_ok, const float* s_bias) {
+template <int KIND, typename Hook, typename PreWrite>
+__device__ __forceinline__ void epi_layer(const ChainParamsDev& p, int l, TeamCtx& t, int u0, uint32_t tl, int tile, int rows_valid,
+                                          bool tile_tma_ok, const float* s_bias, Hook&& before_unit, PreWrite&& before_a_write) {
   constexpr bool kBias = (KIND == EK_BIAS_SOFTPLUS || KIND == EK_BIAS_RELU || KIND == EK_BIAS_GENERIC);
   const ChainLayerDev& L = p.L[l];
   const int nmain = kBias ? L.ncol_out : min(L.ncol_out, L.ncol_main);
@@ -394,9 +400,9 @@ __device__ __forceinline__ void epi_layer(const ChainParamsDev& p, int l, TeamCt
   }
   if (KIND == EK_TANGENT && !(L.out_ops & (1 << OP_OUT2))) fast_ok = false;
   const int n_fast = fast_ok ? L.n_full : 0;
-  int u = team;
-  for (; u < n_fast; u += kTeams) epi_unit<KIND, true>(p, l, t, tl, u, tile, rows_valid, tile_tma_ok, s_bias);
-  for (; u < L.n_units; u += kTeams) epi_unit<KIND, false>(p, l, t, tl, u, tile, rows_valid, tile_tma_ok, s_bias);
+  int u = u0;
+  for (; u < n_fast; u += kTeams) { before_unit(u); epi_unit<KIND, true>(p, l, t, tl, u, tile, rows_valid, tile_tma_ok, s_bias, before_a_write); }
+  for (; u < L.n_units; u += kTeams) { before_unit(u); epi_unit<KIND, false>(p, l, t, tl, u, tile, rows_valid, tile_tma_ok, s_bias, before_a_write); }
 }
 
 // FAM: 0 = bias/activation epilogues (forward chains), 1 = derivative-product epilogues (gradient sweeps), 2 = tangent
@@ -410,9 +416,10 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + kSlotsBytes + kChBiasBytes);
   uint64_t* full = bars;                               // [kWStages]  W stage landed
   uint64_t* empty = bars + kWStages;                   // [kWStages]  W stage consumed
-  uint64_t* a_ready = bars + 2 * kWStages;             // A operand written + accumulator drained (all epilogue warps)
-  uint64_t* acc_ready = bars + 2 * kWStages + 1;       // accumulator of the current layer complete
-  uint64_t* b_in_full = bars + 2 * kWStages + 2;       // [kTeams][kSlotsIn]
+  uint64_t* a_ready = bars + 2 * kWStages;             // [2] next A operand written for K < 128 (+ accumulator half 0 drained) / all of it
+  uint64_t* acc_ready = bars + 2 * kWStages + 2;       // [2] accumulator N half 0 / half 1 of the current layer complete
+  uint64_t* a_free = bars + 2 * kWStages + 4;          // the MMAs of this layer no longer read A columns K < 128
+  uint64_t* b_in_full = bars + 2 * kWStages + 5;       // [kTeams][kSlotsIn]
   uint64_t* b_in_empty = b_in_full + kTeams * kSlotsIn;
   uint64_t* b_out_full = b_in_empty + kTeams * kSlotsIn;   // [kTeams][kSlotsOut]
   uint64_t* b_out_empty = b_out_full + kTeams * kSlotsOut;
@@ -428,7 +435,10 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     if (smem_u32(smem) & 1023u) { printf("nero: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_ready, kChEpiWarps);
+    mbar_init(a_ready + 1, kChEpiWarps);
     mbar_init(acc_ready, 1);
+    mbar_init(acc_ready + 1, 1);
+    mbar_init(a_free, 1);
     for (int i = 0; i < kTeams * kSlotsIn; ++i) { mbar_init(&b_in_full[i], 1); mbar_init(&b_in_empty[i], 4); }
     for (int i = 0; i < kTeams * kSlotsOut; ++i) { mbar_init(&b_out_full[i], 4); mbar_init(&b_out_empty[i], 1); }
     fence_mbar_init();
@@ -476,7 +486,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+      if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(a_ready + 1); }
       for (int l = 0; l < p.n_layers; ++l) {
         const ChainLayerDev& L = p.L[l];
         // bias of this layer -> smem buffer (l & 1): written while the MMAs run; the named barrier below orders it
@@ -487,10 +497,31 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           if (i < 256) sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
         }
         mbar_wait(acc_ready, acc_phase);
-        acc_phase ^= 1;
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
-#define NERO_EPI_CALL(K) epi_layer<K>(p, l, t, team, tl, tile, rows_valid, tile_tma_ok, sb)
+        // The layer runs as two N halves (k_umma: half 0 = accumulator columns [0, h_units*16)): the units of half 0 are
+        // processed while the tensor core still works on half 1, and once this warp has written its part of the next A
+        // operand's columns K < 128 the next layer's first MMAs may start (a_ready[0]) under the rest of this epilogue.
+        const int h_units = (L.n_pad > 128 ? L.n_pad / 2 : L.n_pad) >> 4;
+        const bool hand_over = l + 1 < p.n_layers;
+        bool got_acc1 = false, got_free = false, lo_sent = false;
+        auto before_unit = [&](int u) {
+          if (u >= h_units && !got_acc1) { mbar_wait(acc_ready + 1, acc_phase); tcgen05_fence_after(); got_acc1 = true; }
+          if (u >= 8 && !lo_sent) {      // this warp's share of A columns K < 128 is complete (units ascend)
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0 && hand_over) mbar_arrive(a_ready);
+            lo_sent = true;
+          }
+        };
+        // the next A operand (columns K < 128) is written over the one the half-1 MMAs of THIS layer still read: wait for
+        // them right before the first such write (by then the unit's own math has covered most of that time)
+        auto before_a_write = [&](int u) {
+          if (u < 8 && !got_acc1 && !got_free) { mbar_wait(a_free, acc_phase); tcgen05_fence_after(); got_free = true; }
+        };
+        const int u0 = (team + l) % kTeams;          // rotate the unit -> team assignment so the 16 = 6+5+5 split evens out
+#define NERO_EPI_CALL(K) epi_layer<K>(p, l, t, u0, tl, tile, rows_valid, tile_tma_ok, sb, before_unit, before_a_write)
         if constexpr (FAM == 0) {
           if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
           else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
@@ -503,11 +534,18 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           NERO_EPI_CALL(EK_TANGENT);
         }
 #undef NERO_EPI_CALL
+        // every barrier of the layer is passed exactly once per thread (phase bookkeeping), all MMAs of the layer are done
+        if (!got_acc1) { mbar_wait(acc_ready + 1, acc_phase); tcgen05_fence_after(); }
+        if (!got_free) mbar_wait(a_free, acc_phase);
+        acc_phase ^= 1;
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         // the last layer of a tile hands over nothing: the next tile's A operand is announced after its conversion
-        if (lane == 0 && l + 1 < p.n_layers) mbar_arrive(a_ready);
+        if (lane == 0 && hand_over) {
+          if (!lo_sent) mbar_arrive(a_ready);
+          mbar_arrive(a_ready + 1);
+        }
       }
     }
   } else if (warp == kChMmaWarp) {
@@ -521,13 +559,19 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         const uint32_t half_rows = uint32_t(L.n_pad) / nh;
         const uint32_t idesc = make_idesc_bf16(CH_BM, half_rows);
         const uint32_t b_plane = half_rows * 128u;
-        mbar_wait(a_ready, a_phase);
-        a_phase ^= 1;
-        tcgen05_fence_after();
-        for (int c = 0; c < L.k_chunks; ++c) {
-          for (int hf = 0; hf < nh; ++hf, ++g) {
+        const int kc = L.k_chunks;
+        bool hi_ok = false;
+        for (int hf = 0; hf < nh; ++hf) {
+          const uint32_t d_col = tmem_base + kAccCol + uint32_t(hf) * half_rows;
+          for (int c = 0; c < kc; ++c, ++g) {
+            if (hf == 0 && c == 0) { mbar_wait(a_ready, a_phase); tcgen05_fence_after(); }           // A columns K < 128, half 0 drained
+            // all of A written, half 1 drained.  Also required before this layer's a_free / acc_ready[1] commits are
+            // issued: every epilogue thread passes the previous layer's phase of those barriers before it arrives on
+            // a_ready[1], so waiting here keeps a barrier from completing two phases ahead of a waiter (single-half
+            // layers would otherwise commit them after a_ready[0] alone).
+            const bool commits_late = (hf == nh - 1) && (c == (kc < 2 ? kc : 2) - 1 || c == kc - 1);
+            if (!hi_ok && (c == 2 || hf == 1 || commits_late)) { mbar_wait(a_ready + 1, a_phase); tcgen05_fence_after(); hi_ok = true; }
             const int s = g % kWStages;
-            const uint32_t d_col = tmem_base + kAccCol + uint32_t(hf) * half_rows;
             mbar_wait(&full[s], (g / kWStages) & 1);
             tcgen05_fence_after();
             if (elect_one()) {
@@ -542,11 +586,17 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
                 umma_bf16_ts(d_col, tmem_base + kAHiCol + a_col, dbh, idesc, 1);
               }
               umma_commit(&empty[s]);
-              if (c == L.k_chunks - 1 && hf == nh - 1) umma_commit(acc_ready);
+              const bool last_c = c == kc - 1;
+              if (hf == 0 && last_c) umma_commit(acc_ready);
+              // A columns K < 128 are dead once the last half has passed its K chunks 0 and 1
+              if (hf == nh - 1 && c == (kc < 2 ? kc : 2) - 1) umma_commit(a_free);
+              if (hf == nh - 1 && last_c) umma_commit(acc_ready + 1);
             }
             __syncwarp();
           }
         }
+        if (!hi_ok) { mbar_wait(a_ready + 1, a_phase); tcgen05_fence_after(); }      // keep the phases in step
+        a_phase ^= 1;
       }
     }
   } else if (warp == kChLoadWarp) {
@@ -558,8 +608,8 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         const int nh = L.n_pad > 128 ? 2 : 1;
         const uint32_t half_rows = uint32_t(L.n_pad) / nh;
         const uint32_t plane = uint32_t(L.n_pad) * 128u, hp = half_rows * 128u;
-        for (int c = 0; c < L.k_chunks; ++c) {
-          for (int hf = 0; hf < nh; ++hf, ++g) {
+        for (int hf = 0; hf < nh; ++hf) {
+          for (int c = 0; c < L.k_chunks; ++c, ++g) {
             const int s = g % kWStages;
             mbar_wait(&empty[s], ((g / kWStages) & 1) ^ 1);
             if (elect_one()) {
@@ -598,10 +648,14 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           if (!L.in_ops) continue;
           const CUtensorMap* mh = (L.in_ops & (1 << OP_H)) ? &p.maps[L.map[OP_H]] : nullptr;
           const CUtensorMap* m2 = (L.in_ops & (1 << OP_AUX2)) ? &p.maps[L.map[OP_AUX2]] : nullptr;
-          for (int u = tm; u < L.n_full; u += kTeams) {
+          const CUtensorMap* mc = (L.in_ops & (1 << OP_CSRC)) ? &p.maps[L.map[OP_CSRC]] : nullptr;
+          int u = (tm + l) % kTeams;
+          for (; u < L.n_full; u += kTeams) {
             if (mh) issue(mh, u * 16, r0);
             if (m2) issue(m2, u * 16, r0);
           }
+          if (mc)      // the skip-concat source of the units at and beyond the last valid column
+            for (; u < L.n_units; u += kTeams) issue(mc, u * 16, r0);
         }
       }
     }
@@ -632,7 +686,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           if (!L.out_ops) continue;
           const CUtensorMap* ms = (L.out_ops & (1 << OP_SAVE)) ? &p.maps[L.map[OP_SAVE]] : nullptr;
           const CUtensorMap* m2 = (L.out_ops & (1 << OP_OUT2)) ? &p.maps[L.map[OP_OUT2]] : nullptr;
-          for (int u = tm; u < L.n_full; u += kTeams) {
+          for (int u = (tm + l) % kTeams; u < L.n_full; u += kTeams) {
             if (ms) issue(ms, u * 16, r0);
             if (m2) issue(m2, u * 16, r0);
           }
@@ -749,7 +803,7 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
     struct { int op; const float* ptr; int ld; int cols; bool use; } ops[OP_COUNT] = {
         {OP_H, s.H, s.ldh, nmain, !bias_kind && s.kind != EK_DACT_NONE},
         {OP_AUX2, o.aux2, o.ld2, nmain, !bias_kind},
-        {OP_CSRC, s.csrc, s.ld_csrc, 256, false},        // the skip-concat source is read row by row
+        {OP_CSRC, s.csrc, s.ld_csrc, 256, s.write_a != 0},
         {OP_SAVE, s.save, s.ld_save, nmain, true},
         {OP_OUT2, s.out2, s.ldo2, nmain, tangent}};
     for (auto& q : ops) {
@@ -761,7 +815,7 @@ int chain_dispatch(const ChainParams& p, cudaStream_t stream) {
     }
     const int ncomp = nmain < s.ncol_out ? nmain : s.ncol_out;
     o.n_full = ncomp / 16;
-    o.in_ops = o.n_full ? (o.tma & ((1 << OP_H) | (1 << OP_AUX2))) : 0;
+    o.in_ops = (o.n_full ? (o.tma & ((1 << OP_H) | (1 << OP_AUX2))) : 0) | (o.tma & (1 << OP_CSRC));
     o.out_ops = o.n_full ? (o.tma & ((1 << OP_SAVE) | (1 << OP_OUT2))) : 0;
   }
   static bool attr_set = false;
