@@ -76,7 +76,10 @@ int nero_chain(const void* chain_params_host, void* stream);
 int nero_row_axpy(const float* a, int lda, const float* X, int ldx, float* Y, int ldy, int ncol, const int* m_ptr, int m_cap, void* stream);
 
 /* ---- weight gradients -------------------------------------------------------------------------------------
- * partial[p] = dY^T X (+ dY2^T X2) over the p-th slice of rows; replaces the autograd weight-gradient GEMMs. */
+ * partial += dY^T X (+ dY2^T X2): P CTAs per 128-row output tile each contract a slice of the sample rows and ADD their tile
+ * into the one [rows_partial x ld_partial] fp32 accumulator `partial` (and the column sums of dY into `bias_partial`
+ * [rows_partial]) with L2 reductions; the caller zeroes both before the call.  Replaces the autograd weight-gradient GEMMs;
+ * nero_wgrad_finish is then called with P = 1. */
 int nero_wgrad(const float* dY, int ldy, int n_valid, const float* X, int ldx, int k_valid,
                const float* dY2, int ldy2, const float* X2, int ldx2,
                float* partial, int ld_partial, int rows_partial, float* bias_partial,

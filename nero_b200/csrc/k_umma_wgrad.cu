@@ -5,8 +5,10 @@
 // (packed cvt.rn.bf16x2) and write 8-sample k-chunks (one 16-byte store, bank-conflict free) into the same
 // K-major SWIZZLE_128B layout the linear kernel uses (tile row = feature index, K = sample index).
 // Split-K over CTAs: CTA (p, t) owns a contiguous range of 64-sample chunks of output row tile t, accumulates a
-// 128 x NW fp32 tile in TMEM and writes its partial to HBM; nero_wgrad_finish (k_weights.cu) reduces the partials
-// and applies the weight-norm chain rule.
+// 128 x NW fp32 tile in TMEM and ADDS it into the one [rows x ld] accumulator of the layer with vectorised L2
+// reductions (red.global.add.v4.f32): the accumulator (256 KB) stays L2-resident, there is no [P][rows][ld] partial
+// round trip through HBM any more (round 1: 29 MB written + re-read per layer).  nero_wgrad_finish (k_weights.cu)
+// then applies the weight-norm chain rule to that single matrix.  The caller zeroes the accumulator.
 // The optional second pair implements the double-backward term of the SDF network,
 //   dW_k = abar_k^T h_k + v_k^T ubar_k      (SURVEY.md Appendix A.3, K4),
 // in ONE accumulator.  Column sums of dY (bias gradient) are produced by the dY producer threads for free.
@@ -22,8 +24,8 @@ struct WgradParams {
   const float* dY2; int ldy2; const float* X2; int ldx2;
   int n0; int n_valid;   // output rows [n0 + 128*blockIdx.y, +128) = dY columns; columns >= n_valid read as zero
   int k0; int k_valid;   // output cols [k0, k0+NW) = X columns; columns >= k_valid read as zero
-  float* partial; int ld_partial; int rows_partial;  // [P][rows_partial][ld_partial]
-  float* bias_partial;                               // [P][rows_partial] (may be null)
+  float* partial; int ld_partial; int rows_partial;  // [rows_partial][ld_partial], accumulated into (zeroed by the caller)
+  float* bias_partial;                               // [rows_partial] (may be null), accumulated into
   const int* m_ptr; int m_cap;
 };
 
@@ -77,6 +79,32 @@ __device__ __forceinline__ float store_octets(const float (&x)[NOCT][8], uint8_t
     *reinterpret_cast<uint4*>(plane_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
   return sum;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// epilogue of both kernels: the CTA's 128 x NW accumulator tile (TMEM) is added into the layer's accumulator matrix
+template <int NW>
+__device__ __forceinline__ void wg_epilogue(const WgradParams& p, uint32_t tmem_base, int pw, int lane, int n0, bool any, const float* s_bias) {
+  const int orow = n0 + pw * 32 + lane;
+  float* prow = p.partial + size_t(orow) * p.ld_partial + p.k0;
+  const uint32_t taddr = tmem_base + (uint32_t(pw * 32) << 16);
+  if (any) {
+#pragma unroll 1
+    for (int cc = 0; cc < (NW + 31) / 32; ++cc) {
+      float v[32];
+      tmem_ld32(taddr + cc * 32, v);
+      tmem_ld_wait();
+      if (orow < p.rows_partial) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (cc * 32 + j < NW) red_add_v4(prow + cc * 32 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    if (p.bias_partial && p.k0 == 0 && orow < p.rows_partial) atomicAdd(&p.bias_partial[orow], s_bias[pw * 32 + lane]);
+  }
 }
 
 template <int NW>
@@ -165,30 +193,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
     // every producer warp joins the barrier below (named barrier 1) so that s_bias is complete for the epilogue
     asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
     if (warp < 4) {
-      // -------- epilogue: TMEM -> partial tile in HBM
+      // -------- epilogue: TMEM tile -> added into the layer's accumulator
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
-      const int orow = n0 + pw * 32 + lane;
-      float* prow = p.partial + (size_t(blockIdx.x) * p.rows_partial + orow) * p.ld_partial + p.k0;
-      const uint32_t taddr = tmem_base + (uint32_t(pw * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < (NW + 31) / 32; ++cc) {
-        float v[32];
-        if (nchunks > 0) {
-          tmem_ld32(taddr + cc * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-        }
-        if (orow < p.rows_partial) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (cc * 32 + j < NW) *reinterpret_cast<float4*>(prow + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
-      if (p.bias_partial && p.k0 == 0 && orow < p.rows_partial)
-        p.bias_partial[size_t(blockIdx.x) * p.rows_partial + orow] = s_bias[pw * 32 + lane];
+      wg_epilogue<NW>(p, tmem_base, pw, lane, n0, nchunks > 0, s_bias);
     }
   } else {
     // -------- MMA issuer
@@ -346,31 +354,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
     if (warp < 4) {
-      // -------- epilogue: TMEM -> partial tile in HBM (identical to the transposing kernel)
+      // -------- epilogue: TMEM tile -> added into the layer's accumulator
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
-      const int pw = warp;
-      const int orow = n0 + pw * 32 + lane;
-      float* prow = p.partial + (size_t(blockIdx.x) * p.rows_partial + orow) * p.ld_partial + p.k0;
-      const uint32_t taddr = tmem_base + (uint32_t(pw * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < (NW + 31) / 32; ++cc) {
-        float v[32];
-        if (nchunks > 0) {
-          tmem_ld32(taddr + cc * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-        }
-        if (orow < p.rows_partial) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (cc * 32 + j < NW) *reinterpret_cast<float4*>(prow + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
-      if (p.bias_partial && p.k0 == 0 && orow < p.rows_partial)
-        p.bias_partial[size_t(blockIdx.x) * p.rows_partial + orow] = s_bias[pw * 32 + lane];
+      wg_epilogue<NW>(p, tmem_base, warp, lane, n0, nchunks > 0, s_bias);
     }
   } else {
     // -------- MMA issuer

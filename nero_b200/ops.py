@@ -284,26 +284,26 @@ def _finish_job_dtype():
 
 
 class WgradWorkspace:
-    """Split-K partial buffers of the weight-gradient GEMMs.  With `defer` set (the engines do), every nero_wgrad launch
-    gets its own partial slot and its reduction / weight-norm chain rule is queued; `flush()` runs all queued reductions
-    in ONE nero_wgrad_finish_batch launch.  Jobs that would accumulate into the same gradient rows are never queued
-    together (the queue is flushed first), so the batched kernel has no write conflicts."""
+    """Accumulators of the weight-gradient GEMMs.  nero_wgrad splits the sample rows over `P` CTAs per output tile; each CTA
+    ADDS its tile into one [rows x ld] fp32 accumulator with L2 reductions (no split-K partial round trip through HBM).
+    With `defer` set (the engines do), every nero_wgrad launch gets its own accumulator slot and its weight-norm chain rule is
+    queued; `flush()` runs all queued jobs in ONE nero_wgrad_finish_batch launch and re-zeroes the used slots (one memset).
+    Jobs that would accumulate into the same gradient rows are never queued together (the queue is flushed first), so the
+    batched kernel has no write conflicts."""
 
     def __init__(self, device, P=74, rows=256, ld=384, max_slots=48):
         self.P, self.rows, self.ld = P, rows, ld
         self.device, self.max_slots = device, max_slots
-        self.slots = []
+        # one pool: slot i = acc[i] [rows, ld] followed by its bias sums [rows]; zero = ready to accumulate into
+        self.pool = torch.zeros(max_slots, rows * ld + rows, dtype=torch.float32, device=device)
         self.jobs, self.dest, self.keep = [], set(), []
         self.defer = False
         self._tab = None
-        self._slot()
 
     def _slot(self):
         i = len(self.jobs)
-        while len(self.slots) <= i:
-            self.slots.append((torch.zeros(self.P, self.rows, self.ld, dtype=torch.float32, device=self.device),
-                               torch.zeros(self.P, self.rows, dtype=torch.float32, device=self.device)))
-        return self.slots[i]
+        row = self.pool[i]
+        return row[:self.rows * self.ld].view(1, self.rows, self.ld), row[self.rows * self.ld:].view(1, self.rows)
 
     @property
     def partial(self):
@@ -334,6 +334,7 @@ class WgradWorkspace:
         rc = lib.nero_wgrad_finish_batch(_ptr(self._tab), len(self.jobs), max_rows, max_k, _stream())
         _check(rc, 'nero_wgrad_finish_batch')
         launch_count += 1
+        self.pool[:len(self.jobs)].zero_()          # the used accumulators are ready for the next pass
         self.jobs, self.dest, self.keep = [], set(), []
 
 
@@ -361,6 +362,9 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
         ws.bias_partial[0, :n_valid] = dY.t[:M, dY.c0:dY.c0 + n_valid].sum(0)
     else:
         P = ws.P
+        if not ws.defer and not DRY_RUN:          # stand-alone use: the accumulator slot is zeroed per call
+            partial_t.zero_()
+            bias_t.zero_()
         rc = 0 if DRY_RUN else lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
                             dY2.ptr() if dY2 else None, dY2.ld if dY2 else 0, X2.ptr() if X2 else None, X2.ld if X2 else 0,
                             _ptr(partial_t), ws.ld, ws.rows, _ptr(bias_t), n_rows_pad, k_pad, P, _ptr(m_ptr),
@@ -376,10 +380,10 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
     if ws.defer and DEBUG_GEMM != 'torch':
         ptr = lambda t: 0 if t is None else t.data_ptr()
         job = (ptr(partial_t), ptr(bias_t) if with_bias else 0, ptr(layer.kmap), ptr(w_), ptr(g), ptr(grad_w), ptr(grad_g),
-               ptr(grad_b) if with_bias else 0, 0, ws.P, ws.rows, ws.ld, layer.K, layer.row0, layer.nrows, 1.0, 0.0)
+               ptr(grad_b) if with_bias else 0, 0, 1, ws.rows, ws.ld, layer.K, layer.row0, layer.nrows, 1.0, 0.0)
         ws.enqueue(job, (grad_w.data_ptr(), layer.row0), (w_, g))
         return
-    rc = lib.nero_wgrad_finish(_ptr(partial_t), ws.P, ws.rows, ws.ld, _ptr(bias_t) if with_bias else None,
+    rc = lib.nero_wgrad_finish(_ptr(partial_t), 1, ws.rows, ws.ld, _ptr(bias_t) if with_bias else None,
                                layer.K, layer.row0, layer.nrows, _ptr(layer.kmap), ctypes.c_float(1.0),
                                _ptr(w_), _ptr(g), _ptr(grad_w), _ptr(grad_g),
                                _ptr(grad_b) if with_bias else None, None, ctypes.c_float(0.0), _stream())
