@@ -361,7 +361,8 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
         ws.partial[0, :n_valid, :layer.k_layout] = dw
         ws.bias_partial[0, :n_valid] = dY.t[:M, dY.c0:dY.c0 + n_valid].sum(0)
     else:
-        P = ws.P
+        # row slices per 128-row output tile: all 148 SMs busy also when the layer has a single tile (narrow heads)
+        P = ws.P * 2 // ceil_div(n_rows_pad, 128) if n_rows_pad <= 128 else ws.P
         if not ws.defer and not DRY_RUN:          # stand-alone use: the accumulator slot is zeroed per call
             partial_t.zero_()
             bias_t.zero_()
