@@ -92,6 +92,15 @@ int nero_wgrad_finish(const float* partial, int P, int rows_partial, int ld_part
 int nero_colsum(const float* X, int ldx, int ncol, const float* w, int ldw, const int* m_ptr, int m_cap, float* out,
                 void* stream);
 
+/* ---- stand-alone encodings (fused into their consumers on the training path) --------------------------------
+ * nero_pe : out[i, 0:d(1+2L)] = scale * [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)], d in {3,4}
+ *           (Embedder / get_embedder, network/field.py:14-58).
+ * nero_ide: out[i, 0:72] = integrated directional encoding [Re(36) | Im(36)] of dirs[i, 0:3] with
+ *           kappa_inv[i*kstride] (kappa_inv == NULL: kappa_scalar)   (generate_ide_fn(5), utils/ref_utils.py:53-117;
+ *           needs nero_set_ide_table first). */
+int nero_pe(const float* x, int d, int ldx, int M, int L, float scale, float* out, int ldo, void* stream);
+int nero_ide(const float* dirs, int ldd, const float* kappa_inv, int kstride, float kappa_scalar, int M, float* out, int ldo, void* stream);
+
 /* ---- encodings --------------------------------------------------------------------------------------------
  * Upload the IDE coefficient table mat[17][36] (HOST pointer; fp32-rounded like utils/ref_utils.py:77-82). */
 int nero_set_ide_table(const float* mat17x36_host);
@@ -144,11 +153,11 @@ int nero_composite_bwd(const int* slot, int R, int S, const float* a_in, const f
 
 /* ---- split-sum shading (AppShadingNetwork.forward, network/field.py:591-651; IDE utils/ref_utils.py:85-115) - */
 int nero_shade_prep_fwd(const float* G, const float* pts, const int* ray_in, const float* rays_d, const float* OUTS, float* E, int lde,
-                        float* GEO, const float* human_poses, float* EH, int ldeh, int pos_freq, const int* m_ptr, int m_cap, void* stream);
+                        float* GEO, const float* human_poses, float* EH, int ldeh, int pos_freq, const int* m_ptr, int m_cap, int sphere, void* stream);
 int nero_shade_prep_bwd(const float* G, const float* pts, const int* ray_in, const float* rays_d, const float* OUTS, const float* GEO,
                         const float* dE_dir, int ld_dir, const float* dE_inn, int ld_inn, const float* dE_dif, int ld_dif,
                         const float* dEH, int ld_eh, const float* human_poses, const float* dNoV, float* DOUTS, float* DG,
-                        const int* m_ptr, int m_cap, void* stream);
+                        const int* m_ptr, int m_cap, int sphere, void* stream);
 int nero_shade_combine_fwd(const float* OUTS, const float* GEO, const float* lut, float exp_max, int human, float* color,
                            float* occ_prob, float* refl, const int* m_ptr, int m_cap, void* stream);
 int nero_shade_combine_bwd(const float* OUTS, const float* GEO, const float* lut, float exp_max, int human, const float* dcolor,

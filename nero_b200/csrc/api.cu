@@ -75,6 +75,7 @@ struct ShadePrepParams {
   const float* human_poses; float* EH; int ldeh;
   int pos_freq;
   const int* m_ptr; int m_cap;
+  int sphere;
 };
 struct ShadePrepBwdParams {
   const float* G; const float* pts; const int* ray_in; const float* rays_d; const float* OUTS; const float* GEO;
@@ -82,6 +83,7 @@ struct ShadePrepBwdParams {
   const float* dEH; int ld_eh; const float* human_poses; const float* dNoV;
   float* DOUTS; float* DG;
   const int* m_ptr; int m_cap;
+  int sphere;
 };
 struct ShadeCombineParams {
   const float* OUTS; const float* GEO; const float* lut; float exp_max; int human;
@@ -145,6 +147,8 @@ int mc_combine_bwd(const ::nero_mc_params& q, cudaStream_t st);
 int mc_dir_bwd(const ::nero_mc_params& q, cudaStream_t st);
 int mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ldc, float* Y, int ldy, cudaStream_t st);
 int chain_dispatch(const ChainParams& p, cudaStream_t stream);
+int pe_standalone(const float* x, int d, int ldx, int M, int L, float scale, float* out, int ldo, cudaStream_t st);
+int ide_standalone(const float* dirs, int ldd, const float* kappa, int kstride, float kappa_scalar, int M, float* out, int ldo, cudaStream_t st);
 int occ_loss(const float* occ_prob, const float* gt, const int* sel, const int* p_ptr, int p_cap, float* loss_sum, float* docc_sign,
              cudaStream_t st);
 }  // namespace nero
@@ -241,6 +245,13 @@ int nero_mat_prep(const float* pts, int M, float* X, int ldx, float* CAT, int ld
   return mat_prep(pts, M, X, ldx, CAT, ldc, Y, ldy, (cudaStream_t)stream);
 }
 
+int nero_pe(const float* x, int d, int ldx, int M, int L, float scale, float* out, int ldo, void* stream) {
+  return pe_standalone(x, d, ldx, M, L, scale, out, ldo, (cudaStream_t)stream);
+}
+int nero_ide(const float* dirs, int ldd, const float* kappa_inv, int kstride, float kappa_scalar, int M, float* out, int ldo, void* stream) {
+  return ide_standalone(dirs, ldd, kappa_inv, kstride, kappa_scalar, M, out, ldo, (cudaStream_t)stream);
+}
+
 int nero_chain(const void* chain_params_host, void* stream) {
   if (!chain_params_host) return NERO_ERR_ARG;
   return chain_dispatch(*reinterpret_cast<const ChainParams*>(chain_params_host), (cudaStream_t)stream);
@@ -307,16 +318,16 @@ int nero_composite_bwd(const int* slot, int R, int S, const float* a_in, const f
   return composite_backward(slot, R, S, a_in, c_in, a_out, c_out, drgb, da_in, dc_in, da_out, dc_out, (cudaStream_t)stream);
 }
 int nero_shade_prep_fwd(const float* G, const float* pts, const int* ray_in, const float* rays_d, const float* OUTS, float* E, int lde,
-                        float* GEO, const float* human_poses, float* EH, int ldeh, int pos_freq, const int* m_ptr, int m_cap, void* stream) {
-  ShadePrepParams q{G, pts, ray_in, rays_d, OUTS, E, lde, GEO, human_poses, EH, ldeh, pos_freq, m_ptr, m_cap};
+                        float* GEO, const float* human_poses, float* EH, int ldeh, int pos_freq, const int* m_ptr, int m_cap, int sphere, void* stream) {
+  ShadePrepParams q{G, pts, ray_in, rays_d, OUTS, E, lde, GEO, human_poses, EH, ldeh, pos_freq, m_ptr, m_cap, sphere};
   return shade_prep_forward(q, (cudaStream_t)stream);
 }
 int nero_shade_prep_bwd(const float* G, const float* pts, const int* ray_in, const float* rays_d, const float* OUTS, const float* GEO,
                         const float* dE_dir, int ld_dir, const float* dE_inn, int ld_inn, const float* dE_dif, int ld_dif,
                         const float* dEH, int ld_eh, const float* human_poses, const float* dNoV, float* DOUTS, float* DG,
-                        const int* m_ptr, int m_cap, void* stream) {
+                        const int* m_ptr, int m_cap, int sphere, void* stream) {
   ShadePrepBwdParams q{G, pts, ray_in, rays_d, OUTS, GEO, dE_dir, ld_dir, dE_inn, ld_inn, dE_dif, ld_dif, dEH, ld_eh, human_poses, dNoV,
-                       DOUTS, DG, m_ptr, m_cap};
+                       DOUTS, DG, m_ptr, m_cap, sphere};
   return shade_prep_backward(q, (cudaStream_t)stream);
 }
 int nero_shade_combine_fwd(const float* OUTS, const float* GEO, const float* lut, float exp_max, int human, float* color,

@@ -23,7 +23,7 @@ int set_ide_table_mc(const float* mat17x36_host) {
     for (int m = 0; m <= l; ++m) { t.m[i] = m; t.l[i] = l; ++i; }
   }
   for (int k = 0; k < 17; ++k)
-    for (int j = 0; j < 36; ++j) t.mat[k][j] = double(mat17x36_host[k * 36 + j]);
+    for (int j = 0; j < 36; ++j) { t.mat[k][j] = double(mat17x36_host[k * 36 + j]); t.matf[k][j] = mat17x36_host[k * 36 + j]; }
   NERO_CUDA_TRY(cudaMemcpyToSymbol(c_ide_mc, &t, sizeof(IdeTable)));
   return NERO_OK;
 }

@@ -6,6 +6,9 @@
 //                         of every predictor head for the backward GEMMs.
 // Buffer layouts (mirrored in nero_b200/shape_renderer.py):
 //   E    [N, 240] : PE6(r) @0 (39) | PE8(x) @40 (51) | IDE(r,rough) @92 (72) | IDE(n,1) @164 (72)
+//   E    [N, 384] with sphere_direction (field.py:560-563, 583-586: outer_light reads 144 columns):
+//                   PE6(r) @0 | PE8(x) @40 | IDE(r,rough) @92 | IDE(s_r,rough) @164 | IDE(n,1) @236 | IDE(s_n,1) @308,
+//                   s_d = the direction of the unit-sphere exit point of the ray (x, d)
 //   OUTS [N, 32]  : metallic @0 | roughness @4 | albedo @8 | Ldiffuse @12 | Ldirect @16 | Lindirect @20 | inner_weight @24 | human @28 (4)
 //   GEO  [N, 8]   : n(3) NoV r(3) hit
 #include "common.cuh"
@@ -14,6 +17,7 @@
 namespace nero {
 
 constexpr int E_PE6R = 0, E_PE8X = 40, E_IDER = 92, E_IDEN = 164;
+constexpr int ES_IDESR = 164, ES_IDEN = 236, ES_IDESN = 308;   // sphere_direction layout
 constexpr int O_MET = 0, O_ROUGH = 4, O_ALB = 8, O_LD = 12, O_LDIR = 16, O_LI = 20, O_IW = 24, O_HUM = 28, O_LDIM = 32;
 
 __constant__ IdeTable c_ide;
@@ -26,7 +30,7 @@ int set_ide_table(const float* mat17x36_host) {
     for (int m = 0; m <= l; ++m) { t.m[i] = m; t.l[i] = l; ++i; }
   }
   for (int k = 0; k < 17; ++k)
-    for (int j = 0; j < 36; ++j) t.mat[k][j] = double(mat17x36_host[k * 36 + j]);
+    for (int j = 0; j < 36; ++j) { t.mat[k][j] = double(mat17x36_host[k * 36 + j]); t.matf[k][j] = mat17x36_host[k * 36 + j]; }
   NERO_CUDA_TRY(cudaMemcpyToSymbol(c_ide, &t, sizeof(IdeTable)));
   return NERO_OK;
 }
@@ -42,6 +46,7 @@ struct ShadePrepParams {
   const float* human_poses; float* EH; int ldeh;   // human light (null when disabled)
   int pos_freq;
   const int* m_ptr; int m_cap;
+  int sphere;
 };
 
 __global__ void shade_prep_fwd_kernel(const ShadePrepParams q) {
@@ -67,7 +72,16 @@ __global__ void shade_prep_fwd_kernel(const ShadePrepParams q) {
   ide_forward(c_ide, rf, rough, buf);
   for (int c = 0; c < 72; ++c) e[E_IDER + c] = buf[c];
   ide_forward(c_ide, n, 1.0f, buf);
-  for (int c = 0; c < 72; ++c) e[E_IDEN + c] = buf[c];
+  for (int c = 0; c < 72; ++c) e[(q.sphere ? ES_IDEN : E_IDEN) + c] = buf[c];
+  if (q.sphere) {
+    float sd[3];
+    sphere_dir_fwd(x, rf, sd);
+    ide_forward(c_ide, sd, rough, buf);
+    for (int c = 0; c < 72; ++c) e[ES_IDESR + c] = buf[c];
+    sphere_dir_fwd(x, n, sd);
+    ide_forward(c_ide, sd, 1.0f, buf);
+    for (int c = 0; c < 72; ++c) e[ES_IDESN + c] = buf[c];
+  }
   float hit = 0.f;
   if (q.human_poses) {
     const HumanGeo h = human_geo_fwd(x, rf, q.human_poses + size_t(r) * 12, rough);
@@ -84,14 +98,15 @@ __global__ void shade_prep_fwd_kernel(const ShadePrepParams q) {
 
 struct ShadePrepBwdParams {
   const float* G; const float* pts; const int* ray_in; const float* rays_d; const float* OUTS; const float* GEO;
-  const float* dE_dir; int ld_dir;   // d IDE(r,rough) from outer_light(direct)   cols [0,72)
+  const float* dE_dir; int ld_dir;   // d IDE(r,rough) from outer_light(direct)   cols [0,72)  [+ d IDE(s_r,rough) cols [72,144)]
   const float* dE_inn; int ld_inn;   // d IDE(r,rough) from inner_light          cols [0,72)
-  const float* dE_dif; int ld_dif;   // d IDE(n,1)     from outer_light(diffuse) cols [0,72)
+  const float* dE_dif; int ld_dif;   // d IDE(n,1)     from outer_light(diffuse) cols [0,72)  [+ d IDE(s_n,1) cols [72,144)]
   const float* dEH; int ld_eh;       // d IPE (24)     from the human predictor  (null when disabled)
   const float* human_poses;
   const float* dNoV;
   float* DOUTS; float* DG;
   const int* m_ptr; int m_cap;
+  int sphere;
 };
 
 __global__ void shade_prep_bwd_kernel(const ShadePrepBwdParams q) {
@@ -114,6 +129,18 @@ __global__ void shade_prep_bwd_kernel(const ShadePrepBwdParams q) {
   float drough = ide_backward(c_ide, rf, rough, dide, dr);
   for (int c = 0; c < 72; ++c) dide[c] = q.dE_dif[size_t(i) * q.ld_dif + c];
   ide_backward(c_ide, n, 1.0f, dide, dnrm);
+  if (q.sphere) {      // the second halves of the two outer_light inputs: encodings of the sphere exit directions
+    float sd[3], dsd[3] = {0.f, 0.f, 0.f};
+    sphere_dir_fwd(x, rf, sd);
+    for (int c = 0; c < 72; ++c) dide[c] = q.dE_dir[size_t(i) * q.ld_dir + 72 + c];
+    drough += ide_backward(c_ide, sd, rough, dide, dsd);
+    sphere_dir_bwd(x, rf, dsd, dr);
+    sphere_dir_fwd(x, n, sd);
+    dsd[0] = dsd[1] = dsd[2] = 0.f;
+    for (int c = 0; c < 72; ++c) dide[c] = q.dE_dif[size_t(i) * q.ld_dif + 72 + c];
+    ide_backward(c_ide, sd, 1.0f, dide, dsd);
+    sphere_dir_bwd(x, n, dsd, dnrm);
+  }
   if (q.human_poses) {
     const float* pose = q.human_poses + size_t(r) * 12;
     const HumanGeo h = human_geo_fwd(x, rf, pose, rough);
@@ -193,6 +220,37 @@ __global__ void shade_combine_bwd_kernel(const ShadeCombineParams q) {
   }
   q.dNoV[i] = d.NoV;
 }
+
+constexpr int kEncBlock = 128;
+// out[i, 0:72] = IDE(dirs[i, 0:3], kappa_inv[i * kstride])   (kappa == nullptr: kappa_scalar for every row)
+__global__ void __launch_bounds__(kEncBlock) ide_kernel(const float* __restrict__ dirs, int ldd, const float* __restrict__ kappa, int kstride,
+                                                       float kappa_scalar, int M, float* __restrict__ out, int ldo) {
+  __shared__ float s_rows[kEncBlock * 73];
+  const int i0 = blockIdx.x * kEncBlock;
+  const int i = i0 + threadIdx.x;
+  if (i < M) {
+    const float d[3] = {dirs[size_t(i) * ldd], dirs[size_t(i) * ldd + 1], dirs[size_t(i) * ldd + 2]};
+    ide_forward(c_ide, d, kappa ? kappa[size_t(i) * kstride] : kappa_scalar, s_rows + threadIdx.x * 73);
+  }
+  __syncthreads();
+  const int rows = min(kEncBlock, M - i0);
+  if (ldo == 72) {
+    float* dst = out + size_t(i0) * 72;
+    for (int e = threadIdx.x; e < rows * 72; e += kEncBlock) dst[e] = s_rows[(e / 72) * 73 + e % 72];
+  } else {
+    for (int r = threadIdx.x >> 5; r < rows; r += kEncBlock / 32)
+      for (int c = threadIdx.x & 31; c < 72; c += 32) out[size_t(i0 + r) * ldo + c] = s_rows[r * 73 + c];
+  }
+}
+
+int ide_standalone(const float* dirs, int ldd, const float* kappa, int kstride, float kappa_scalar, int M, float* out, int ldo, cudaStream_t st) {
+  if (!dirs || !out || ldd < 3 || ldo < 72) return NERO_ERR_ARG;
+  if (M <= 0) return NERO_OK;
+  ide_kernel<<<(M + kEncBlock - 1) / kEncBlock, kEncBlock, 0, st>>>(dirs, ldd, kappa, kstride, kappa_scalar, M, out, ldo);
+  NERO_LAUNCH_CHECK();
+  return NERO_OK;
+}
+
 
 static inline int blocks_for(long n, int per) { return int((n + per - 1) / per); }
 

@@ -53,10 +53,15 @@ NERO_HD void pe_tangent(const float* pe, int L, const float* d, float* t, float 
 
 // ---------------------------------------------------------------- integrated directional encoding
 // utils/ref_utils.py:53-117.  36 (m,l) pairs: l in {1,2,4,8,16}, m = 0..l.  out = [Re(36) | Im(36)].
-// The z-polynomials P_i(z) = sum_k mat[k][i] z^k are evaluated by Horner in fp64 from the reference's
-// fp32-rounded coefficient table (the reference evaluates them in fp32 as Vandermonde @ mat).
+// The z-polynomials P_i(z) = sum_k mat[k][i] z^k are ill-conditioned near |z| = 1 in fp32 (the l = 16 band cancels ~1e5 :
+// the reference's own result is up to 2.4e-3 away from exact arithmetic there), so the VALUE is evaluated exactly the way
+// the reference evaluates it -- verified bit for bit against torch on 7e5 entries (oracle/make_golden.py, round 2):
+//   * vmz[k] = z**k is the correctly rounded fp32 power (torch.pow): here the fp64 power rounded to fp32;
+//   * torch.matmul(vmz, mat) on the CPU accumulates k = 0..16 in ascending order with one fp32 FMA per term.
+// The backward pass (no bit-level reference exists for it) differentiates the exact polynomial: Horner in fp64.
 struct IdeTable {
   double mat[17][36];
+  float matf[17][36];
   int m[36];
   int l[36];
 };
@@ -70,18 +75,31 @@ NERO_HD void ide_poly(const IdeTable& T, int i, double z, double& P, double& dP)
   }
   P = p; dP = dp;
 }
+// vmz[k] = fp32(z^k), k = 0..16
+NERO_HD void ide_powers(float z, float* pw) {
+  double p = 1.0;
+  const double zd = double(z);
+  for (int k = 0; k <= 16; ++k) { pw[k] = float(p); p *= zd; }
+}
+// the reference's fp32 value of P_i(z): ascending-k FMA chain over the Vandermonde row
+NERO_HD float ide_poly_value(const IdeTable& T, int i, const float* pw) {
+  const int deg = T.l[i] - T.m[i];
+  float acc = 0.0f;
+  for (int k = 0; k <= deg; ++k) acc = fmaf(pw[k], T.matf[k][i], acc);
+  return acc;
+}
 
 NERO_HD void ide_forward(const IdeTable& T, const float* d, float kappa_inv, float* out) {
-  float pr[17], pi[17];
+  float pr[17], pi[17], pw[17];
   pr[0] = 1.0f; pi[0] = 0.0f;
   for (int m = 1; m <= 16; ++m) { pr[m] = pr[m - 1] * d[0] - pi[m - 1] * d[1]; pi[m] = pr[m - 1] * d[1] + pi[m - 1] * d[0]; }
+  ide_powers(d[2], pw);
   for (int i = 0; i < 36; ++i) {
-    double P, dP;
-    ide_poly(T, i, double(d[2]), P, dP);
+    const float P = ide_poly_value(T, i, pw);
     const float sigma = 0.5f * float(T.l[i] * (T.l[i] + 1));
-    const float a = float(P) * expf(-sigma * kappa_inv);
-    out[i] = pr[T.m[i]] * a;
-    out[36 + i] = pi[T.m[i]] * a;
+    const float att = expf(-sigma * kappa_inv);
+    out[i] = (pr[T.m[i]] * P) * att;
+    out[36 + i] = (pi[T.m[i]] * P) * att;
   }
 }
 // dout[72] -> dd[3] (accumulated into), dkappa (returned)

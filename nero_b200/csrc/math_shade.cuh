@@ -67,6 +67,40 @@ NERO_HD void shade_geometry_bwd(const float* g, const float* n, const float* v, 
   for (int c = 0; c < 3; ++c) dg[c] += (dn[c] - dnn * n[c]) / gn;
 }
 
+// ------------------------------------------------------------------ sphere_direction light encoding (network/field.py:380-396, 560-563, 583-586)
+// s = normalize(p' + d t): the unit-sphere exit point of the ray (p', d), p' = p pulled back to radius 0.999 when it lies
+// outside (offset_points_to_sphere), t = -p'.d + sqrt((p'.d)^2 - |p'|^2 + 1 + 1e-6) (get_sphere_intersection).
+NERO_HD void sphere_dir_fwd(const float* p_raw, const float* d, float* s) {
+  float p[3] = {p_raw[0], p_raw[1], p_raw[2]};
+  const float pn = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  if (pn > 0.999f) { for (int c = 0; c < 3; ++c) { p[c] /= pn; p[c] *= 0.999f; } }
+  const float dtx = p[0] * d[0] + p[1] * d[1] + p[2] * d[2], xtx = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+  const float t = -dtx + sqrtf(dtx * dtx - xtx + 1.0f + 1e-6f);
+  float q[3];
+  for (int c = 0; c < 3; ++c) q[c] = p[c] + d[c] * t;
+  const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), 1e-12f);
+  for (int c = 0; c < 3; ++c) s[c] = q[c] / qn;
+}
+// (ds/dd)^T gs accumulated into gd (the point is a constant of the render)
+NERO_HD void sphere_dir_bwd(const float* p_raw, const float* d, const float* gs, float* gd) {
+  float p[3] = {p_raw[0], p_raw[1], p_raw[2]};
+  const float pn = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  if (pn > 0.999f) { for (int c = 0; c < 3; ++c) { p[c] /= pn; p[c] *= 0.999f; } }
+  const float dtx = p[0] * d[0] + p[1] * d[1] + p[2] * d[2], xtx = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+  const float root = sqrtf(dtx * dtx - xtx + 1.0f + 1e-6f);
+  const float t = -dtx + root;
+  float q[3];
+  for (int c = 0; c < 3; ++c) q[c] = p[c] + d[c] * t;
+  const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), 1e-12f);
+  float s[3], gq[3];
+  for (int c = 0; c < 3; ++c) s[c] = q[c] / qn;
+  const float gss = gs[0] * s[0] + gs[1] * s[1] + gs[2] * s[2];
+  for (int c = 0; c < 3; ++c) gq[c] = (gs[c] - gss * s[c]) / qn;
+  const float gt = gq[0] * d[0] + gq[1] * d[1] + gq[2] * d[2];
+  const float dt_ddtx = -1.0f + dtx / root;
+  for (int c = 0; c < 3; ++c) gd[c] += gq[c] * t + gt * dt_ddtx * p[c];
+}
+
 // ------------------------------------------------------------------ split-sum combine   (network/field.py:601-623, :571-576)
 struct ShadeIn {
   float metallic, roughness, albedo[3];

@@ -478,8 +478,6 @@ class ShapeEngine:
         dev = params.deviation_network.variance.device
         assert dev.type == 'cuda' or ops.DRY_RUN, 'nero_b200 runs on a CUDA device only (no CPU fallback)'
         self.dev = dev
-        if self.scfg['sphere_direction']:
-            raise NotImplementedError('sphere_direction=True is not implemented in the B200 path')
         if self.scfg['light_pos_freq'] != 8:
             raise NotImplementedError('light_pos_freq != 8')
         upload_ide_table()
@@ -491,7 +489,12 @@ class ShapeEngine:
         self.m_met = Predictor(c.metallic_predictor, dev, 1, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
         self.m_rough = Predictor(c.roughness_predictor, dev, 1, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
         self.m_alb = Predictor(c.albedo_predictor, dev, 3, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
-        self.m_outer = Predictor(c.outer_light, dev, 3, ACT_EXPCLAMP, self.exp_max, k_layout=72, t_cols=(0, 72))
+        # sphere_direction (field.py:560-563, 583-586): outer_light reads [IDE(d, k) | IDE(s_d, k)], s_d = direction of the
+        # unit-sphere exit point of the ray (x, d); the E buffer then holds the two 144-wide windows (k_shade.cu)
+        self.sphere = bool(self.scfg['sphere_direction'])
+        self.e_iden, self.e_ld = (236, 384) if self.sphere else (E_IDEN, E_LD)
+        ko = 144 if self.sphere else 72
+        self.m_outer = Predictor(c.outer_light, dev, 3, ACT_EXPCLAMP, self.exp_max, k_layout=ko, t_cols=(0, ko))
         self.m_inner = Predictor(c.inner_light, dev, 3, ACT_EXPCLAMP, self.exp_max,
                                  kmap=list(range(51)) + [52 + i for i in range(72)], k_layout=124, t_cols=(52, 72))
         self.m_iw = Predictor(c.inner_weight, dev, 1, ACT_NONE, kmap=[40 + i for i in range(51)] + list(range(39)), k_layout=91)
@@ -547,7 +550,7 @@ class ShapeEngine:
                  n_in=z(1, dt=torch.int32), n_out=z(1, dt=torch.int32), slot=z(R, S, dt=torch.int32))
         # inner
         w.update(X0=z(cap, 64), PTS=z(cap, 4), RAY_IN=z(cap, dt=torch.int32), Y8=z(cap, Y8_LD), U0=z(cap, 64), USKIP=z(cap, 64),
-                 G=z(cap, 4), OUTS=z(cap, O_LDIM), E=z(cap, E_LD), GEO=z(cap, 8), EH=z(cap, 64), COLOR_IN=z(cap, 4), OCCP=z(cap),
+                 G=z(cap, 4), OUTS=z(cap, O_LDIM), E=z(cap, self.e_ld), GEO=z(cap, 8), EH=z(cap, 64), COLOR_IN=z(cap, 4), OCCP=z(cap),
                  REFL=z(cap, 4), ALPHA_IN=z(cap), GERR=z(cap))
         w['H'] = [None] + [z(cap, 256) for _ in range(8)]
         w['V'] = [z(cap, 256) for _ in range(8)]
@@ -602,8 +605,8 @@ class ShapeEngine:
         cap = R * S
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
         w = self.w
-        w.update(dALPHA_IN=z(cap), dCOLOR_IN=z(cap, 4), DOUTS=z(cap, O_LDIM), DNOV=z(cap), dE_dir=z(cap, 128), dE_inn=z(cap, 128),
-                 dE_dif=z(cap, 128), dEH=z(cap, 64), DG=z(cap, 4), dY8=z(cap, Y8_LD), dHa=z(cap, 256), dHb=z(cap, 256), dHc=z(cap, 256),
+        w.update(dALPHA_IN=z(cap), dCOLOR_IN=z(cap, 4), DOUTS=z(cap, O_LDIM), DNOV=z(cap), dE_dir=z(cap, 160), dE_inn=z(cap, 128),
+                 dE_dif=z(cap, 160), dEH=z(cap, 64), DG=z(cap, 4), dY8=z(cap, Y8_LD), dHa=z(cap, 256), dHb=z(cap, 256), dHc=z(cap, 256),
                  D_INV_S=z(1))
         w['UB'] = [z(cap, 64)] + [z(cap, 256) for _ in range(8)]
         w['ABAR'] = [z(cap, 256) for _ in range(8)]
@@ -732,10 +735,10 @@ class ShapeEngine:
         self.m_alb.forward(matin, A['alb'], Mat(w['OUTS'], O_ALB), n_in, cap)
         hp = human_poses.contiguous() if self.human else None
         self._hp = hp
-        K('nero_shade_prep_fwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['E'], E_LD, w['GEO'], hp, w['EH'] if self.human else None,
-          64, 8, n_in, cap)
+        K('nero_shade_prep_fwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['E'], self.e_ld, w['GEO'], hp, w['EH'] if self.human else None,
+          64, 8, n_in, cap, 1 if self.sphere else 0)
         self.m_outer.forward(Mat(w['E'], E_IDER), A['odir'], Mat(w['OUTS'], O_LDIR), n_in, cap)
-        self.m_outer.forward(Mat(w['E'], E_IDEN), A['odif'], Mat(w['OUTS'], O_LD), n_in, cap)
+        self.m_outer.forward(Mat(w['E'], self.e_iden), A['odif'], Mat(w['OUTS'], O_LD), n_in, cap)
         self.m_inner.forward(Mat(w['E'], E_PE8X), A['inner'], Mat(w['OUTS'], O_LI), n_in, cap)
         self.m_iw.forward(Mat(w['E'], 0), A['iw'], Mat(w['OUTS'], O_IW), n_in, cap)
         if self.human:
@@ -766,6 +769,34 @@ class ShapeEngine:
             self.sdf.sdf_only(q['X0'], q['SA'], q['SB'], q['SC'], q['OUT'], None, n)
             out[c0:c0 + n] = q['OUT'][:n]
         return out.reshape(*shape, 1)
+
+    # ------------------------------------------------------------------ per-point materials (renderer.py:629-647 -> field.py:653-657)
+    def materials_query(self, x):
+        """(metallic [M,1], roughness [M,1], albedo [M,3]) of arbitrary points: the SDF feature vector (sdf_network(x)[:, 1:])
+        through the three material predictors -- forward only, chunked through the training workspaces."""
+        x = x.reshape(-1, 3).to(self.dev, torch.float32).contiguous()
+        M = x.shape[0]
+        if self.w is None:
+            self._alloc(self.cfg['test_ray_num'], self.cfg['n_samples'] + self.cfg['n_importance'] + self.cfg['n_bg_samples'])
+        w = self.w
+        chunk = w['X0'].shape[0]
+        out = torch.empty(M, 5, device=self.dev)
+        A = w['ACT']
+        for c0 in range(0, M, chunk):
+            n = min(chunk, M - c0)
+            K('nero_points_fill', x[c0:c0 + n], n, w['PTS'], w['RAY_IN'], w['X0'], 64, w['Y8'], Y8_LD, w['H'][4], 256)
+            H = w['H']
+            self.sdf.hidden_forward(w['X0'], [H[1], H[2], H[3], H[4], H[5], H[6], H[7], H[8]], H[4], None, n, save=False,
+                                    heads=[CL(self.sdf.L8f, EK_BIAS_GENERIC, 256, save=Mat(w['Y8']), write_a=False)])
+            matin = Mat(w['Y8'])
+            self.m_met.forward(matin, A['met'], Mat(w['OUTS'], O_MET), None, n)
+            self.m_rough.forward(matin, A['rough'], Mat(w['OUTS'], O_ROUGH), None, n)
+            self.m_alb.forward(matin, A['alb'], Mat(w['OUTS'], O_ALB), None, n)
+            o = w['OUTS'][:n]
+            out[c0:c0 + n, 0] = o[:, O_MET]
+            out[c0:c0 + n, 1] = o[:, O_ROUGH]
+            out[c0:c0 + n, 2:5] = o[:, O_ALB:O_ALB + 3]
+        return out[:, 0:1], out[:, 1:2], out[:, 2:5]
 
     # ------------------------------------------------------------------ validation extras (renderer.py:465-482)
     def validation_info(self, rays_o, rays_d, z_vals, human_poses):
@@ -860,14 +891,15 @@ class ShapeEngine:
           w['DNOV'], n_in, cap)
         A = w['ACT']
         dHa, dHb, dHc = w['dHa'], w['dHb'], w['dHc']
-        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LDIR), Mat(w['E'], E_IDER), A['odir'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dir']), dx_ncol=72, dHc=dHc)
-        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LD), Mat(w['E'], E_IDEN), A['odif'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dif']), dx_ncol=72, dHc=dHc)
+        ko = 144 if self.sphere else 72
+        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LDIR), Mat(w['E'], E_IDER), A['odir'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dir']), dx_ncol=ko, dHc=dHc)
+        self.m_outer.backward(ws, Mat(w['DOUTS'], O_LD), Mat(w['E'], self.e_iden), A['odif'], dHa, dHb, n_in, cap, dX=Mat(w['dE_dif']), dx_ncol=ko, dHc=dHc)
         self.m_inner.backward(ws, Mat(w['DOUTS'], O_LI), Mat(w['E'], E_PE8X), A['inner'], dHa, dHb, n_in, cap, dX=Mat(w['dE_inn']), dx_ncol=72, dHc=dHc)
         self.m_iw.backward(ws, Mat(w['DOUTS'], O_IW), Mat(w['E'], 0), A['iw'], dHa, dHb, n_in, cap, dHc=dHc)
         if self.human:
             self.m_human.backward(ws, Mat(w['DOUTS'], O_HUM), Mat(w['EH']), A['human'], dHa, dHb, n_in, cap, dX=Mat(w['dEH']), dx_ncol=24, dHc=dHc)
-        K('nero_shade_prep_bwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['GEO'], w['dE_dir'], 128, w['dE_inn'], 128, w['dE_dif'], 128,
-          w['dEH'] if self.human else None, 64, st['hp'], w['DNOV'], w['DOUTS'], w['DG'], n_in, cap)
+        K('nero_shade_prep_bwd', w['G'], w['PTS'], w['RAY_IN'], rays_d, w['OUTS'], w['GEO'], w['dE_dir'], 160, w['dE_inn'], 128, w['dE_dif'], 160,
+          w['dEH'] if self.human else None, 64, st['hp'], w['DNOV'], w['DOUTS'], w['DG'], n_in, cap, 1 if self.sphere else 0)
         matin = Mat(w['Y8'])
         self.m_rough.backward(ws, Mat(w['DOUTS'], O_ROUGH), matin, A['rough'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dHc=dHc)
         self.m_met.backward(ws, Mat(w['DOUTS'], O_MET), matin, A['met'], dHa, dHb, n_in, cap, dX=Mat(w['dY8']), dx_ncol=256, dx_addend=Mat(w['dY8']), dHc=dHc)

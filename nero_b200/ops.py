@@ -430,6 +430,37 @@ def K(name, *args):
     launch_count += 1
 
 
+# ------------------------------------------------------------------------------------------------ stand-alone encodings
+def positional_encoding(x, L, scale=1.0):
+    """get_embedder(L, d)[0](x) (network/field.py:14-58) for d = 3 or 4 on the CUDA path: [M, d] -> [M, d(1+2L)]."""
+    global launch_count
+    x = x.contiguous().float()
+    M, d = x.shape
+    out = torch.empty(M, d * (1 + 2 * L), device=x.device)
+    rc = lib.nero_pe(_ptr(x), d, d, M, L, ctypes.c_float(scale), _ptr(out), out.shape[1], _stream())
+    _check(rc, 'nero_pe')
+    launch_count += 1
+    return out
+
+
+def integrated_dir_enc(dirs, kappa_inv):
+    """generate_ide_fn(5)(dirs, kappa_inv) (utils/ref_utils.py:53-117) on the CUDA path: [M,3], [M,1] or float -> [M,72]."""
+    global launch_count
+    from .engine import upload_ide_table
+    upload_ide_table()
+    dirs = dirs.contiguous().float()
+    M = dirs.shape[0]
+    out = torch.empty(M, 72, device=dirs.device)
+    if torch.is_tensor(kappa_inv):
+        k = kappa_inv.reshape(-1).contiguous().float()
+        rc = lib.nero_ide(_ptr(dirs), 3, _ptr(k), 1, ctypes.c_float(0.0), M, _ptr(out), 72, _stream())
+    else:
+        rc = lib.nero_ide(_ptr(dirs), 3, None, 0, ctypes.c_float(float(kappa_inv)), M, _ptr(out), 72, _stream())
+    _check(rc, 'nero_ide')
+    launch_count += 1
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ fused MLP chain
 EK_BIAS_SOFTPLUS, EK_BIAS_RELU, EK_BIAS_GENERIC, EK_DACT_SOFTPLUS, EK_DACT_RELU, EK_DACT_NONE, EK_TANGENT = range(7)
 

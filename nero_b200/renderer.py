@@ -320,9 +320,56 @@ class NeROShapeRenderer(nn.Module):
         return outputs
 
     def forward(self, data):
-        if 'eval' in data:        # network/renderer.py:319-330
-            return self.test_step(int(data['index']) if not isinstance(data['index'], int) else data['index'], step=data['step'])
+        if 'eval' in data:        # network/renderer.py:608-627
+            index = int(data['index']) if not isinstance(data['index'], int) else data['index']
+            outputs = self.test_step(index, step=data['step'])
+            if index == 0 and self.cfg['val_geometry']:       # network/renderer.py:618-623
+                outputs['vertices'], outputs['triangles'] = self.extract_geometry(resolution=128, threshold=0.0)
+            return outputs
         return self.train_step(data['step'])
+
+    # ------------------------------------------------------------------ geometry / material export hooks
+    def extract_fields(self, bound_min=(-1.0, -1.0, -1.0), bound_max=(1.0, 1.0, 1.0), resolution=128, outside_val=1.0):
+        """The SDF sampled on a regular grid, 1.0 outside the unit sphere (extract_fields, network/field.py:1090-1104); the
+        whole grid goes through the forward-only CUDA chain in one chunked query instead of 64^3 blocks."""
+        dev = self.deviation_network.variance.device
+        axes = [torch.linspace(float(bound_min[i]), float(bound_max[i]), resolution, device=dev) for i in range(3)]
+        xx, yy, zz = torch.meshgrid(*axes, indexing='ij')
+        pts = torch.stack([xx, yy, zz], -1).reshape(-1, 3)
+        with torch.no_grad():
+            val = self.engine.sdf_query(pts)[:, 0]
+        val = torch.where(torch.norm(pts, dim=-1) >= 1.0, torch.full_like(val, float(outside_val)), val)
+        return val.reshape(resolution, resolution, resolution).cpu().numpy()
+
+    def extract_geometry(self, bound_min=(-1.0, -1.0, -1.0), bound_max=(1.0, 1.0, 1.0), resolution=128, threshold=0.0):
+        """extract_geometry (network/field.py:1106-1113): marching cubes on the field; the cubes stay third party (PyMCubes,
+        as in the reference) and are imported here, where they are needed."""
+        u = self.extract_fields(bound_min, bound_max, resolution)
+        import mcubes                 # noqa: the host repo's dependency (requirements.txt of the reference)
+        vertices, triangles = mcubes.marching_cubes(u, threshold)
+        bmin, bmax = np.asarray(bound_min, np.float32), np.asarray(bound_max, np.float32)
+        vertices = vertices / (resolution - 1.0) * (bmax - bmin)[None, :] + bmin[None, :]
+        return vertices, triangles
+
+    def predict_materials(self, xyz=None, batch_size=8192):
+        """Per-vertex metallic / roughness / albedo of the extracted mesh (network/renderer.py:629-647): SDF feature vector ->
+        color_network.predict_materials (field.py:653-657).  `xyz` [V,3] supplies the vertices directly; by default they are
+        read from data/meshes/{cfg['name']}-300000.ply like the reference does."""
+        if xyz is None:
+            from .material import read_ply
+            xyz, _ = read_ply(f"data/meshes/{self.cfg['name']}-300000.ply")
+        dev = self.deviation_network.variance.device
+        xyz = torch.as_tensor(np.asarray(xyz, np.float32) if not torch.is_tensor(xyz) else xyz).to(dev)
+        e = self.engine
+        e.prepare_weights()
+        outs = {'metallic': [], 'roughness': [], 'albedo': []}
+        with torch.no_grad():
+            for vi in range(0, xyz.shape[0], batch_size):
+                m, r, a = e.materials_query(xyz[vi:vi + batch_size])
+                outs['metallic'].append(m.cpu().numpy())
+                outs['roughness'].append(r.cpu().numpy())
+                outs['albedo'].append(a.cpu().numpy())
+        return {k: np.concatenate(v, 0) for k, v in outs.items()}
 
 
 def _material_renderer(*a, **k):

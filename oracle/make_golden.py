@@ -206,6 +206,44 @@ def make_material_fixture(name, cfg, P, steps, seed=6033, pseed=7):
     print(name, 'saved; loss', {s: float(out[f's{s}_loss']) for s in steps}, 'keys', sorted(o.keys()))
 
 
+def make_round2_fixtures(seed=6033, pseed=7):
+    """Round 2: stage-I sphere_direction lighting (field.py:560-563, 583-586), NeROShapeRenderer.predict_materials
+    (renderer.py:629-647 -> field.py:653-657), the SDF field of extract_fields (field.py:1090-1104, val_geometry /
+    extract_mesh.py) and the IDE of directions within 1e-3 of the poles (ref_utils.py:85-115)."""
+    make_shape_fixture('shape_sphere_r16', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'sphere_direction': True}}, 16,
+                       [500, 30000])
+    # ---- predict_materials + extract_fields on the perturbed bell parameters
+    cfg = {'n_samples': 32, 'n_importance': 32}
+    net = ref_shim.build_reference_shape_renderer(cfg, seed=seed)
+    sd = O.perturb_params({k: v.detach().clone() for k, v in net.state_dict().items()}, seed=pseed)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(21)
+    xyz = torch.nn.functional.normalize(torch.randn(300, 3, generator=g), dim=-1) * (0.3 + 0.4 * torch.rand(300, 1, generator=g))
+    with torch.no_grad():
+        feats = net.sdf_network(xyz)[:, 1:]
+        m, r, a = net.color_network.predict_materials(xyz, feats)
+        from network.field import extract_fields
+        u = extract_fields(-torch.ones(3), torch.ones(3), 24, lambda x: net.sdf_network.sdf(x), batch_size=16)
+    out = {'param_checksums': param_checksums(sd), 'seed': seed, 'pseed': pseed, 'xyz': xyz, 'metallic': m, 'roughness': r, 'albedo': a,
+           'field24': u}
+    np.savez_compressed(os.path.join(GOLD, 'shape_materials_field.npz'), **npy(out))
+    print('shape_materials_field saved: metallic', float(m.mean()), 'roughness', float(r.mean()), 'field min', float(u.min()))
+    # ---- IDE near the poles: directions within 1e-3 (and 1e-2, 5e-2) of +-z, roughness 0 / 0.3 / 1
+    from utils.ref_utils import generate_ide_fn
+    ide = generate_ide_fn(5)
+    eps = torch.tensor([1e-4, 3e-4, 1e-3, 1e-2, 5e-2])
+    az = torch.linspace(0.1, 6.0, 8)
+    dirs = []
+    for sgn in (1.0, -1.0):
+        for e in eps:
+            for a_ in az:
+                dirs.append(torch.tensor([torch.sin(e) * torch.cos(a_), torch.sin(e) * torch.sin(a_), sgn * torch.cos(e)]))
+    dirs = torch.stack(dirs).float()
+    kap = torch.tensor([0.0, 0.3, 1.0]).repeat(dirs.shape[0] // 3 + 1)[:dirs.shape[0], None]
+    np.savez_compressed(os.path.join(GOLD, 'kat_ide_poles.npz'), **npy({'dirs': dirs, 'kappa': kap, 'ide': ide(dirs, kap)}))
+    print('kat_ide_poles saved', dirs.shape)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     make_encoding_kats()
@@ -217,12 +255,16 @@ def main():
     make_validation_fixture('shape_val_bear_r24', {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}}, 24, 30000)
     for k, (cfg, P, steps) in MATERIAL_FIXTURES.items():
         make_material_fixture(k, cfg, P, steps)
+    make_round2_fixtures()
 
 
 if __name__ == '__main__':
     if '--material-only' in sys.argv:
         for k, (cfg, P, steps) in MATERIAL_FIXTURES.items():
             make_material_fixture(k, cfg, P, steps)
+    elif '--round2-only' in sys.argv:
+        ref_shim.install()
+        make_round2_fixtures()
     elif '--val-only' in sys.argv:
         ref_shim.install()
         make_validation_fixture('shape_val_bell_r32', {'n_samples': 32, 'n_importance': 32}, 32, 30000)

@@ -39,8 +39,10 @@ FIXTURE_CFGS = {
     'shape_bell_r32': {'n_samples': 32, 'n_importance': 32},
     'shape_bear_r24': {'n_samples': 32, 'n_importance': 32, 'shader_config': {'human_light': True}},
     'shape_bell_full_r16': {},
+    'shape_sphere_r16': {'n_samples': 32, 'n_importance': 32, 'shader_config': {'sphere_direction': True}},
 }
-FIXTURE_STEPS = {'shape_bell_r32': [500, 10000, 30000], 'shape_bear_r24': [500, 30000], 'shape_bell_full_r16': [30000]}
+FIXTURE_STEPS = {'shape_bell_r32': [500, 10000, 30000], 'shape_bear_r24': [500, 30000], 'shape_bell_full_r16': [30000],
+                 'shape_sphere_r16': [500, 30000]}
 VAL_FIXTURES = {'shape_val_bell_r32': FIXTURE_CFGS['shape_bell_r32'], 'shape_val_bear_r24': FIXTURE_CFGS['shape_bear_r24']}
 MATERIAL_FIXTURES = {
     'material_bell_p24': ({'shader_cfg': {'human_lights': False, 'diffuse_sample_num': 32, 'specular_sample_num': 16}}, [500, 5000]),

@@ -10,7 +10,7 @@ extern "C" {
 void hc_set_ide(const float* mat) {
   int i = 0;
   for (int e = 0; e < 5; ++e) { int l = 1 << e; for (int m = 0; m <= l; ++m) { g_tab.m[i] = m; g_tab.l[i] = l; ++i; } }
-  for (int k = 0; k < 17; ++k) for (int j = 0; j < 36; ++j) g_tab.mat[k][j] = double(mat[k * 36 + j]);
+  for (int k = 0; k < 17; ++k) for (int j = 0; j < 36; ++j) { g_tab.mat[k][j] = double(mat[k * 36 + j]); g_tab.matf[k][j] = mat[k * 36 + j]; }
 }
 void hc_ide(int n, const float* d, const float* kap, const float* dout, float* out, float* dd, float* dk) {
   for (int i = 0; i < n; ++i) {

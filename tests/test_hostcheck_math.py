@@ -54,12 +54,30 @@ def test_ide(hc):
     (want * dout.double()).sum().backward()
     out, gd, gk = np.zeros((n, 72), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
     hc.hc_ide(n, P(f32(d)), P(f32(kap[:, 0])), P(f32(dout)), P(out), P(gd), P(gk))
-    close(out, want, 2e-5, 2e-5, 'ide value vs fp64 oracle')
+    # the VALUE follows the reference's own fp32 arithmetic (correctly rounded z powers, ascending FMA chain; math_enc.cuh):
+    # it agrees with the fp32 oracle (bit-exact to the reference) to the rounding of the (x+iy)^m recurrence and expf, and
+    # therefore carries the reference's l=16 cancellation error against exact arithmetic
+    w32 = O.ide(d, kap)
+    # (residual: torch evaluates (x+iy)^m as exp(m log z) in fp32, 4e-6 absolute away from the exact power; the kernel's
+    # recurrence is accurate to 3e-7 -- measured in round 2)
+    close(out, w32, 1e-5, 1.2e-5, 'ide value vs the reference arithmetic')
+    assert np.abs(out - want.detach().numpy()).max() < 2e-2
     close(gd, dd.grad, 1e-4, 5e-4, 'ide d/ddir')
     close(gk, kk.grad[:, 0], 1e-4, 5e-4, 'ide d/dkappa')
-    # against the fp32 oracle (the reference's own arithmetic) the high bands carry the reference's cancellation error
-    w32 = O.ide(d, kap)
-    assert np.abs(out - w32.numpy()).max() < 2e-2
+
+
+def test_ide_near_the_poles_matches_the_reference(hc):
+    """Directions within 1e-4 .. 5e-2 of +-z, roughness 0 / 0.3 / 1: the l = 16 band of the reference is up to 2.4e-3 away
+    from exact arithmetic there (fixture from the unmodified reference, oracle/make_golden.py --round2-only)."""
+    from helpers import load_golden
+    gp = load_golden('kat_ide_poles')
+    n = gp['dirs'].shape[0]
+    out, gd, gk = np.zeros((n, 72), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+    dout = np.zeros((n, 72), np.float32)
+    hc.hc_ide(n, P(f32(gp['dirs'])), P(f32(gp['kappa'][:, 0])), P(dout), P(out), P(gd), P(gk))
+    close(out, gp['ide'], 1e-5, 1.2e-5, 'ide at the poles vs the reference')
+    exact = O.ide(torch.from_numpy(gp['dirs']).double(), torch.from_numpy(gp['kappa']).double()).numpy()
+    assert np.abs(gp['ide'] - exact).max() > 1e-3, 'the fixture must exercise the cancellation regime'
 
 
 def test_pe(hc):

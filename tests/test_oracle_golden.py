@@ -72,6 +72,29 @@ def test_shape_fixture(name):
                 np.testing.assert_allclose(p[k.split('::')[1]].grad.numpy(), g[k], rtol=1e-4, atol=1e-7)
 
 
+def test_materials_field_and_pole_fixtures():
+    """Round-2 fixtures of the unmodified reference: color_network.predict_materials on sdf_network features
+    (renderer.py:629-647), the extract_fields grid (field.py:1090-1104) and the IDE near the poles."""
+    g = load_golden('shape_materials_field')
+    cfg = {'n_samples': 32, 'n_importance': 32}
+    sd = build_params(cfg, int(g['seed']), int(g['pseed']))
+    np.testing.assert_allclose(param_checksums(sd), g['param_checksums'], rtol=1e-12)
+    xyz = t(g['xyz'])
+    with torch.no_grad():
+        y = O.sdf_forward(sd, xyz)
+        fin = torch.cat([y[:, 1:], xyz], -1)
+        for k in ('metallic', 'roughness', 'albedo'):
+            got = O.predictor(sd, f'color_network.{k}_predictor', fin, 'sigmoid')
+            np.testing.assert_allclose(got.numpy(), g[k], rtol=1e-5, atol=1e-6, err_msg=k)
+        ax = torch.linspace(-1, 1, 24)
+        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing='ij'), -1).reshape(-1, 3)
+        val = O.sdf_forward(sd, pts)[:, 0]
+        val = torch.where(torch.norm(pts, dim=-1) >= 1.0, torch.ones_like(val), val).reshape(24, 24, 24)
+    np.testing.assert_allclose(val.numpy(), g['field24'], rtol=1e-5, atol=2e-6)
+    gp = load_golden('kat_ide_poles')
+    np.testing.assert_allclose(O.ide(t(gp['dirs']), t(gp['kappa'])).numpy(), gp['ide'], rtol=0, atol=1e-6)
+
+
 @pytest.mark.parametrize('name', list(VAL_FIXTURES))
 def test_validation_fixture(name):
     """is_train=False render (network/renderer.py:465-482) of the oracle vs the unmodified reference."""

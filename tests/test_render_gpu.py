@@ -164,3 +164,41 @@ def test_sdf_grid_query_matches_oracle():
     # chunk boundary / tail: same values when queried alone
     again = net.sdf_network.sdf(x[131000:].to(DEV))
     assert torch.equal(again, got[131000:])
+
+
+def test_predict_materials_and_sdf_field_match_reference():
+    """NeROShapeRenderer.predict_materials (network/renderer.py:629-647) and the extract_fields grid behind val_geometry /
+    extract_mesh.py (field.py:1090-1104) against the unmodified reference."""
+    from nero_b200.renderer import NeROShapeRenderer
+    g = load_golden('shape_materials_field')
+    cfg = {'n_samples': 32, 'n_importance': 32}
+    net = NeROShapeRenderer(cfg, training=False)
+    net.load_state_dict(build_params(cfg, int(g['seed']), int(g['pseed'])))
+    net = net.cuda()
+    pm = net.predict_materials(g['xyz'], batch_size=128)          # several chunks, ragged tail
+    assert pm['albedo'].shape == (300, 3) and pm['metallic'].shape == (300, 1)
+    for k in ('metallic', 'roughness', 'albedo'):
+        allclose(torch.from_numpy(pm[k]), g[k], 1e-4, 1e-5, k)
+    u = net.extract_fields(resolution=24)
+    allclose(torch.from_numpy(u), g['field24'], 1e-4, 2e-5, 'sdf field')
+    net.cfg['val_geometry'] = True
+    try:
+        import mcubes  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):       # the marching-cubes step is the host repo's third-party dependency
+            net.extract_geometry(resolution=16)
+
+
+def test_standalone_encodings_match_reference():
+    """nero_pe / nero_ide (the stand-alone entry points of the encodings) against the reference KATs, including directions
+    within 1e-4 .. 5e-2 of the poles where the reference's fp32 l=16 band is 2.4e-3 away from exact arithmetic."""
+    from nero_b200 import ops
+    g = load_golden('kat_encodings')
+    x = t(g['x']).to(DEV)
+    for L in (4, 6, 8):
+        allclose(ops.positional_encoding(x, L), g[f'pe{L}'], 1e-5, 2e-6, f'pe{L}')
+    allclose(ops.positional_encoding(t(g['x4']).to(DEV), 10), g['pe10_4'], 1e-5, 4e-5, 'pe10 (4-d)')     # sin(512 x): argument rounding
+    allclose(ops.integrated_dir_enc(t(g['ide_dirs']).to(DEV), t(g['ide_kappa']).to(DEV)), g['ide'], 1e-5, 1.2e-5, 'ide')
+    gp = load_golden('kat_ide_poles')
+    allclose(ops.integrated_dir_enc(t(gp['dirs']).to(DEV), t(gp['kappa']).to(DEV)), gp['ide'], 1e-5, 1.2e-5, 'ide near the poles')
+    allclose(ops.integrated_dir_enc(t(gp['dirs']).to(DEV), 0.0), O.ide(t(gp['dirs']), torch.zeros(1, 1)).numpy(), 1e-5, 1.2e-5, 'ide, scalar kappa')
