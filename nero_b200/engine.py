@@ -61,9 +61,8 @@ def upload_ide_table():
     global _ide_uploaded
     if not _ide_uploaded:
         mat = ide_coefficient_table()
-        if not ops.DRY_RUN:
-            rc = ops.lib.nero_set_ide_table(mat.ctypes.data_as(ops.ctypes.c_void_p))
-            ops._check(rc, 'nero_set_ide_table')
+        rc = ops.lib.nero_set_ide_table(mat.ctypes.data_as(ops.ctypes.c_void_p))
+        ops._check(rc, 'nero_set_ide_table')
         _ide_uploaded = True
 
 
@@ -476,7 +475,7 @@ class ShapeEngine:
         self.cfg = cfg
         self.scfg = params.color_network.cfg
         dev = params.deviation_network.variance.device
-        assert dev.type == 'cuda' or ops.DRY_RUN, 'nero_b200 runs on a CUDA device only (no CPU fallback)'
+        ops.require_cuda(dev)
         self.dev = dev
         if self.scfg['light_pos_freq'] != 8:
             raise NotImplementedError('light_pos_freq != 8')
@@ -678,15 +677,10 @@ class ShapeEngine:
         if occ_on:
             K('nero_occ_select', w['PTS'], w['Y8'], Y8_LD, Y8_SDF, w['G'], w['RAY_IN'], rays_d, float(cfg['occ_sdf_thresh']), n_in, cap,
               w['SEL'], w['OCC_COUNT'])
-        if ops.DRY_RUN:
-            w['n_in'].fill_(100)
-            w['OCC_COUNT'].fill_(min(3000, cap))
         with_reg = step < 1000
         if with_reg:
             self.reg_forward(rays_o, rays_d, z_vals)
             w = self.w
-            if ops.DRY_RUN:
-                w['REG_N'].fill_(50)
         counts = torch.cat([w['n_in'], w['OCC_COUNT'], w['REG_N'] if with_reg else w['n_out']]).tolist()   # the one host sync
         N_in = counts[0]
         self.n_reg = counts[2] if with_reg else 0

@@ -130,7 +130,7 @@ class MaterialEngine:
     """Owns the BVH, the prepared tensor-core operands of every stage-II MLP and the per-step workspaces."""
 
     def __init__(self, shader: MCShadingParams, verts, tris, dev):
-        assert dev.type == 'cuda' or ops.DRY_RUN, 'nero_b200 runs on a CUDA device only (no CPU fallback)'
+        ops.require_cuda(dev)
         self.p, self.dev = shader, dev
         c = self.cfg = shader.cfg
         if c['outer_light_version'] not in ('direction', 'sphere_direction'):
@@ -145,13 +145,9 @@ class MaterialEngine:
         self.tab_s = shader.specular_direction_samples.to(dev).contiguous()
         # geometry
         self.verts, self.tris = np.ascontiguousarray(verts, np.float32), np.ascontiguousarray(tris, np.int32)
-        if ops.DRY_RUN:
-            self.bvh_nodes = torch.zeros(1, 32, dtype=torch.uint8)
-            self.bvh_tris = torch.zeros(self.tris.shape[0], 12)
-        else:
-            nodes, tri, _ = ops.bvh_build(self.verts, self.tris)
-            self.bvh_nodes = torch.from_numpy(nodes).to(dev)
-            self.bvh_tris = torch.from_numpy(tri).to(dev)
+        nodes, tri, _ = ops.bvh_build(self.verts, self.tris)
+        self.bvh_nodes = torch.from_numpy(nodes).to(dev)
+        self.bvh_tris = torch.from_numpy(tri).to(dev)
         # networks
         self.feats = FeatsNet(shader.feats_network, dev)
         self.m_met = Predictor(shader.metallic_predictor, dev, 1, ACT_SIGMOID, k_layout=259, t_cols=(0, 256))
@@ -287,8 +283,6 @@ class MaterialEngine:
         ops.mc('nero_mc_sample', q)
         K('nero_bvh_trace', self.bvh_nodes, self.bvh_tris, N, w['ORG'], 4, w['DIR'], 4, w['POSD'], w['NRMH'], MISS_DEPTH, 1)
         ops.mc('nero_mc_classify', q)
-        if ops.DRY_RUN:
-            w['COUNTS'][0], w['COUNTS'][1] = N // 4, N - N // 4
         n_hit, n_miss = w['COUNTS'].tolist()            # the one host sync of the step
         st.update(n_hit=n_hit, n_miss=n_miss)
         ops.mc('nero_mc_fill', q)
@@ -389,8 +383,7 @@ class NeROMaterialRenderer(nn.Module):
     def engine(self):
         if self._engine is None:
             dev = self.shader_network.light_pts.device
-            if dev.type != 'cuda' and not ops.DRY_RUN:
-                raise RuntimeError('NeROMaterialRenderer needs a CUDA device: call .cuda() first (no CPU fallback)')
+            ops.require_cuda(dev, 'NeROMaterialRenderer')
             self._engine = MaterialEngine(self.shader_network, self._mesh[0], self._mesh[1], dev)
         return self._engine
 

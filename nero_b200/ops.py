@@ -1,11 +1,8 @@
 """ctypes bindings of libnero_b200.so + thin tensor-level wrappers.
 
-The product path has NO fallback: importing this module without the built library raises, and every wrapper
-launches a hand-written sm_100a kernel through the C ABI declared in include/nero_b200.h.
-
-NERO_DEBUG_GEMM=torch (tests only) swaps the tcgen05 GEMMs for an fp32 torch emulation OF THE SAME EPILOGUES so
-that test failures can be bisected between "GEMM kernel" and "everything else"; it is never enabled by the
-package itself and bench.py / smoke() refuse to run with it.
+The product path has NO fallback and no alternate backend: importing this module without the built library raises, and
+every wrapper launches a hand-written sm_100a kernel through the C ABI declared in include/nero_b200.h.  (The CPU walk of
+the host logic used by the test-suite lives in tests/dry_run_harness.py and works by substituting `lib` from outside.)
 """
 import ctypes
 import os
@@ -25,8 +22,12 @@ if not os.path.exists(_LIB_PATH):
 lib = ctypes.CDLL(_LIB_PATH)
 
 launch_count = 0  # kernels launched through the C ABI (bench.py reports it)
-DEBUG_GEMM = os.environ.get('NERO_DEBUG_GEMM', '')
-DRY_RUN = bool(os.environ.get('NERO_DRY_RUN'))   # tests only: walk the host logic on CPU tensors without launching
+
+
+def require_cuda(dev, what='nero_b200'):
+    """The kernels run on a CUDA device only: there is no CPU path to fall back to."""
+    if torch.device(dev).type != 'cuda':
+        raise RuntimeError(f'{what} runs on a CUDA device only (move the module with .cuda(); there is no CPU fallback)')
 
 
 def _ptr(t):
@@ -36,8 +37,6 @@ def _ptr(t):
 
 
 def _stream():
-    if DRY_RUN:
-        return ctypes.c_void_p(0)
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -92,8 +91,6 @@ class PreparedLayer:
         global launch_count
         w = self.weight.detach()
         g = None if self.g is None else self.g.detach()
-        if DRY_RUN:
-            return
         rc = lib.nero_prep_weight(_ptr(w), _ptr(g), self.K, self.row0, self.nrows, _ptr(self.kmap), ctypes.c_float(1.0),
                                   _ptr(self.img_f), self.n_pad, _ptr(self.img_t), self.t_npad if self.img_t is not None else 0,
                                   self.t_cols[0] if self.t_cols else 0, self.t_cols[1] if self.t_cols else 0,
@@ -103,16 +100,6 @@ class PreparedLayer:
 
     def bias_view(self):
         return None if self.bias is None else self.bias.detach()[self.row0:self.row0 + self.nrows]
-
-    # fp32 layout-space weights for the debug emulation
-    def w_layout(self):
-        W = self.w_eff[self.row0:self.row0 + self.nrows]
-        if self.kmap is None and self.k_layout == self.K:
-            return W
-        out = torch.zeros(self.nrows, self.k_layout, device=W.device)
-        idx = self.kmap.long() if self.kmap is not None else torch.arange(self.K, device=W.device)
-        out[:, idx] = W
-        return out
 
 
 _PREP_JOB = None
@@ -134,7 +121,7 @@ class PrepBatch:
 
     def run(self):
         global _PREP_JOB, launch_count
-        if DRY_RUN or not self.layers:
+        if not self.layers:
             return
         import numpy as np
         if _PREP_JOB is None:
@@ -153,35 +140,6 @@ class PrepBatch:
         rc = lib.nero_prep_weight_batch(_ptr(self.tab), len(self.layers), self.max_rows, _stream())
         _check(rc, 'nero_prep_weight_batch')
         launch_count += 1
-
-
-def _m_of(m_ptr, m_cap):
-    return m_cap if m_ptr is None else min(int(m_ptr.item()), m_cap)
-
-
-def _dact(h, dact):
-    if dact == ACT_SOFTPLUS100:
-        return torch.where(100 * h > 20, torch.ones_like(h), -torch.expm1(-100 * h))
-    if dact == ACT_RELU:
-        return (h > 0).float()
-    return torch.ones_like(h)
-
-
-def _act(x, act, p):
-    if act == ACT_SOFTPLUS100:
-        return torch.nn.functional.softplus(x, beta=100)
-    if act == ACT_RELU:
-        return torch.relu(x)
-    if act == ACT_SIGMOID:
-        return torch.sigmoid(x)
-    if act == ACT_EXPCLAMP:
-        return torch.exp(torch.clamp(x, max=p))
-    return x
-
-
-def view2d(t, col0, ld=None):
-    """(tensor, column offset) -> (data_ptr with offset, leading dimension)"""
-    return t, col0
 
 
 class Mat:
@@ -219,14 +177,6 @@ def linear(A: Mat, layer: PreparedLayer, out: Mat, ncol_out, *, transposed=False
         bias = layer.bias_view() if use_bias else None
     if m_cap is None:
         m_cap = A.t.shape[0]
-    if DEBUG_GEMM == 'torch':
-        return _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, oscale, H, hscale, dact, V, out2,
-                             addend, ncol_main, tail, m_ptr, m_cap, bias, k_valid)
-    if DRY_RUN:
-        assert A.ld % 4 == 0 and A.c0 % 4 == 0 and ncol_out <= n_pad and img is not None
-        assert A.c0 + k_valid <= A.t.shape[1] and out.c0 + ncol_out <= out.t.shape[1], (A.c0, k_valid, A.t.shape, out.c0, ncol_out, out.t.shape)
-        assert mode != EPI_TANGENT or (H is not None and V is not None and out2 is not None)
-        return
     rc = lib.nero_linear(A.ptr(), A.ld, k_valid, _ptr(img), n_pad, k_chunks, _ptr(bias), 0 if bias is None else bias.numel(), out.ptr(), out.ld, ncol_out,
                          ctypes.c_float(oscale), mode, act, ctypes.c_float(act_param),
                          H.ptr() if H else None, H.ld if H else 0, ctypes.c_float(hscale), dact,
@@ -235,37 +185,6 @@ def linear(A: Mat, layer: PreparedLayer, out: Mat, ncol_out, *, transposed=False
                          tail.ptr() if tail else None, tail.ld if tail else 0, _ptr(m_ptr), m_cap, _stream())
     _check(rc, 'nero_linear')
     launch_count += 1
-
-
-def _linear_torch(A, layer, out, ncol_out, transposed, mode, act, act_param, oscale, H, hscale, dact, V, out2, addend,
-                  ncol_main, tail, m_ptr, m_cap, bias, k_valid):
-    M = _m_of(m_ptr, m_cap)
-    if M == 0:
-        return
-    Wl = layer.w_layout()                       # [nrows, k_layout]
-    if transposed:
-        c0, nc = layer.t_cols
-        a = A.t[:M, A.c0:A.c0 + layer.nrows]
-        acc = a @ Wl[:, c0:c0 + nc]             # [M, nc]
-    else:
-        a = A.t[:M, A.c0:A.c0 + layer.k_layout]
-        acc = a @ Wl.t()
-    acc = acc[:, :ncol_out]
-    if mode == EPI_BIAS_ACT:
-        if bias is not None:
-            acc = acc + bias[:ncol_out]
-        out.t[:M, out.c0:out.c0 + ncol_out] = oscale * _act(acc, act, act_param)
-        return
-    nm = min(ncol_main, ncol_out)
-    s = _dact(H.t[:M, H.c0:H.c0 + nm] * hscale, dact) if H is not None else torch.ones_like(acc[:, :nm])
-    r = oscale * s * acc[:, :nm]
-    if addend is not None:
-        r = r + addend.t[:M, addend.c0:addend.c0 + nm]
-    if mode == EPI_TANGENT:
-        out2.t[:M, out2.c0:out2.c0 + nm] = 100.0 * (1.0 - s) * V.t[:M, V.c0:V.c0 + nm] * acc[:, :nm]
-    out.t[:M, out.c0:out.c0 + nm] = r
-    if tail is not None and ncol_out > ncol_main:
-        tail.t[:M, tail.c0:tail.c0 + ncol_out - ncol_main] = oscale * acc[:, ncol_main:]
 
 
 _FINISH_JOB = None
@@ -351,34 +270,20 @@ def wgrad(ws: WgradWorkspace, dY: Mat, n_valid, X: Mat, k_valid, layer: Prepared
     if ws.defer and grad_w is not None and (grad_w.data_ptr(), layer.row0) in ws.dest:
         ws.flush()                      # a queued job already accumulates into these rows
     partial_t, bias_t = ws.partial, ws.bias_partial
-    if DEBUG_GEMM == 'torch':
-        M = _m_of(m_ptr, m_cap)
-        dw = dY.t[:M, dY.c0:dY.c0 + n_valid].t() @ X.t[:M, X.c0:X.c0 + layer.k_layout]
-        if dY2 is not None:
-            dw = dw + dY2.t[:M, dY2.c0:dY2.c0 + n_valid].t() @ X2.t[:M, X2.c0:X2.c0 + layer.k_layout]
-        ws.partial.zero_()
-        ws.bias_partial.zero_()
-        ws.partial[0, :n_valid, :layer.k_layout] = dw
-        ws.bias_partial[0, :n_valid] = dY.t[:M, dY.c0:dY.c0 + n_valid].sum(0)
-    else:
-        # row slices per 128-row output tile: all 148 SMs busy also when the layer has a single tile (narrow heads)
-        P = ws.P * 2 // ceil_div(n_rows_pad, 128) if n_rows_pad <= 128 else ws.P
-        if not ws.defer and not DRY_RUN:          # stand-alone use: the accumulator slot is zeroed per call
-            partial_t.zero_()
-            bias_t.zero_()
-        rc = 0 if DRY_RUN else lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
-                            dY2.ptr() if dY2 else None, dY2.ld if dY2 else 0, X2.ptr() if X2 else None, X2.ld if X2 else 0,
-                            _ptr(partial_t), ws.ld, ws.rows, _ptr(bias_t), n_rows_pad, k_pad, P, _ptr(m_ptr),
-                            m_cap, _stream())
-        _check(rc, 'nero_wgrad')
-        launch_count += ceil_div(n_rows_pad, 128) * max(1, ceil_div(k_pad, 256))
+    # row slices per 128-row output tile: all 148 SMs busy also when the layer has a single tile (narrow heads)
+    P = ws.P * 2 // ceil_div(n_rows_pad, 128) if n_rows_pad <= 128 else ws.P
+    if not ws.defer:          # stand-alone use: the accumulator slot is zeroed per call
+        partial_t.zero_()
+        bias_t.zero_()
+    rc = lib.nero_wgrad(dY.ptr(), dY.ld, n_valid, X.ptr(), X.ld, k_valid,
+                        dY2.ptr() if dY2 else None, dY2.ld if dY2 else 0, X2.ptr() if X2 else None, X2.ld if X2 else 0,
+                        _ptr(partial_t), ws.ld, ws.rows, _ptr(bias_t), n_rows_pad, k_pad, P, _ptr(m_ptr),
+                        m_cap, _stream())
+    _check(rc, 'nero_wgrad')
+    launch_count += ceil_div(n_rows_pad, 128) * max(1, ceil_div(k_pad, 256))
     g = None if layer.g is None else layer.g.detach()
-    if DRY_RUN:
-        assert grad_w is not None and (grad_b is not None or not with_bias) and (g is None or grad_g is not None)
-        assert dY.c0 + n_valid <= dY.t.shape[1] and X.c0 + k_valid <= X.t.shape[1], (dY.c0, n_valid, dY.t.shape, X.c0, k_valid, X.t.shape)
-        return
     w_ = layer.weight.detach()
-    if ws.defer and DEBUG_GEMM != 'torch':
+    if ws.defer:
         ptr = lambda t: 0 if t is None else t.data_ptr()
         job = (ptr(partial_t), ptr(bias_t) if with_bias else 0, ptr(layer.kmap), ptr(w_), ptr(g), ptr(grad_w), ptr(grad_g),
                ptr(grad_b) if with_bias else 0, 0, 1, ws.rows, ws.ld, layer.K, layer.row0, layer.nrows, 1.0, 0.0)
@@ -396,8 +301,6 @@ def colsum(X: Mat, ncol, out, w: Mat = None, m_ptr=None, m_cap=None):
     global launch_count
     if m_cap is None:
         m_cap = X.t.shape[0]
-    if DRY_RUN:
-        return
     rc = lib.nero_colsum(X.ptr(), X.ld, ncol, w.ptr() if w else None, w.ld if w else 0, _ptr(m_ptr), m_cap, _ptr(out),
                          _stream())
     _check(rc, 'nero_colsum')
@@ -422,9 +325,6 @@ def K(name, *args):
             conv.append(a)
         else:
             conv.append(int(a))
-    if DRY_RUN:
-        getattr(lib, name)
-        return
     rc = getattr(lib, name)(*conv, _stream())
     _check(rc, name)
     launch_count += 1
@@ -510,8 +410,6 @@ def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None, tag=''):
     assert 1 <= len(layers) <= 10
     if m_cap is None:
         m_cap = A0.t.shape[0]
-    if DEBUG_GEMM == 'torch':
-        return _chain_unfused(A0, k_valid0, layers, m_ptr, m_cap)
     P = _ChainParams()
     P.A0, P.lda0, P.k_valid0 = _p(A0), A0.ld, ceil_div(k_valid0, 4) * 4
     P.n_layers, P.m_ptr, P.m_cap = len(layers), _p(m_ptr), m_cap
@@ -538,15 +436,6 @@ def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None, tag=''):
         if nxt is not None:
             nk = nxt.t_chunks if layers[i + 1]['transposed'] else nxt.k_chunks
             L.a_blocks = 4 * nk
-        if DRY_RUN:
-            assert img is not None
-            if d['kind'] in (EK_DACT_SOFTPLUS, EK_DACT_RELU, EK_TANGENT):
-                assert d['H'] is not None
-            if d['kind'] == EK_TANGENT:
-                assert d['V'] is not None and d['out2'] is not None
-    if DRY_RUN:
-        assert A0.c0 % 4 == 0 and A0.ld % 4 == 0 and A0.c0 + P.k_valid0 <= A0.t.shape[1]
-        return
     if PROFILE is not None:
         fl = 0.0
         for d in layers:
@@ -561,32 +450,6 @@ def chain(A0: Mat, k_valid0, layers, m_ptr=None, m_cap=None, tag=''):
     if PROFILE is not None:
         e1.record()
         PROFILE.append((tag, e0, e1, fl, None if m_ptr is None else m_ptr.data_ptr(), m_cap))
-
-
-def _chain_unfused(A0, k_valid0, layers, m_ptr, m_cap):
-    """Debug emulation: the same chain as separate (emulated) linear calls through a scratch buffer."""
-    dev = A0.t.device
-    cur = Mat(torch.zeros(m_cap, 256, device=dev))
-    M = _m_of(m_ptr, m_cap)
-    cur.t[:M, :k_valid0] = A0.t[:M, A0.c0:A0.c0 + k_valid0]
-    kind2mode = {EK_BIAS_SOFTPLUS: (EPI_BIAS_ACT, ACT_SOFTPLUS100, ACT_NONE), EK_BIAS_RELU: (EPI_BIAS_ACT, ACT_RELU, ACT_NONE),
-                 EK_BIAS_GENERIC: (EPI_BIAS_ACT, None, ACT_NONE), EK_DACT_SOFTPLUS: (EPI_MUL_DACT, ACT_NONE, ACT_SOFTPLUS100),
-                 EK_DACT_RELU: (EPI_MUL_DACT, ACT_NONE, ACT_RELU), EK_DACT_NONE: (EPI_MUL_DACT, ACT_NONE, ACT_NONE),
-                 EK_TANGENT: (EPI_TANGENT, ACT_NONE, ACT_SOFTPLUS100)}
-    for i, d in enumerate(layers):
-        mode, act, dact = kind2mode[d['kind']]
-        act = d['act'] if act is None else act
-        out = d['save'] if d['save'] is not None else Mat(torch.zeros(m_cap, 256, device=dev))
-        linear(cur, d['layer'], out, d['ncol_out'], transposed=d['transposed'], mode=mode, act=act, act_param=d['act_param'],
-               oscale=d['oscale'], H=d['H'], hscale=d['hscale'], dact=dact, V=d['V'], out2=d['out2'], addend=d['addend'],
-               ncol_main=d['ncol_main'], tail=d['tail'], m_ptr=m_ptr, m_cap=m_cap, use_bias=d['use_bias'])
-        if d['write_a'] and i + 1 < len(layers):
-            nm = d['ncol_out'] if mode == EPI_BIAS_ACT else min(d['ncol_out'], d['ncol_main'])
-            nxt = torch.zeros(m_cap, 256, device=dev)
-            nxt[:M, :nm] = out.t[:M, out.c0:out.c0 + nm]
-            if d['csrc'] is not None:
-                nxt[:M, nm:256] = d['csrc'].t[:M, d['csrc'].c0 + nm:d['csrc'].c0 + 256]
-            cur = Mat(nxt)
 
 
 # ------------------------------------------------------------------------------------------------ stage II (k_mcshade.cu, k_bvh.cu)
@@ -616,9 +479,6 @@ class McParams(ctypes.Structure):
 def mc(name, params: McParams):
     """Launch one of the nero_mc_* kernels on the current stream."""
     global launch_count
-    if DRY_RUN:
-        getattr(lib, name)
-        return
     rc = getattr(lib, name)(ctypes.byref(params), _stream())
     _check(rc, name)
     launch_count += 1

@@ -20,7 +20,7 @@ class FlatAdam(torch.optim.Optimizer):
         params = [p for p in net.parameters()]
         assert params and all(p.dtype == torch.float32 for p in params)
         dev = params[0].device
-        assert dev.type == 'cuda' or ops.DRY_RUN, 'FlatAdam updates device buffers: move the renderer to CUDA first'
+        ops.require_cuda(dev, 'FlatAdam')
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.net = net
         self.params = params

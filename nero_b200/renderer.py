@@ -90,8 +90,7 @@ class NeROShapeRenderer(nn.Module):
         if self._engine is None:
             from .engine import ShapeEngine
             from . import ops as _ops
-            if self.deviation_network.variance.device.type != 'cuda' and not _ops.DRY_RUN:
-                raise RuntimeError('NeROShapeRenderer must be moved to a CUDA device (.cuda()) -- there is no CPU path')
+            _ops.require_cuda(self.deviation_network.variance.device, 'NeROShapeRenderer')
             self._engine = ShapeEngine(self, self.cfg)
         return self._engine
 

@@ -62,3 +62,25 @@ def material_batch_from_golden(g, dtype=torch.float32):
 
 def material_rands(g, step, dtype=torch.float32):
     return {k: t(g[f's{step}_{k}'], dtype) for k in ('rand_d', 'rand_s', 'rand_ang', 'rand_eps')}
+
+
+def act_ref(x, act, p=0.0):
+    """fp64/fp32 torch reference of the GEMM epilogue activations (codes of include/nero_b200.h)."""
+    if act == 1:
+        return torch.nn.functional.softplus(x, beta=100)
+    if act == 2:
+        return torch.relu(x)
+    if act == 3:
+        return torch.sigmoid(x)
+    if act == 4:
+        return torch.exp(torch.clamp(x, max=p))
+    return x
+
+
+def dact_ref(h, dact):
+    """derivative factor recovered from the stored post-activation value"""
+    if dact == 1:
+        return torch.where(100 * h > 20, torch.ones_like(h), -torch.expm1(-100 * h))
+    if dact == 2:
+        return (h > 0).to(h.dtype)
+    return torch.ones_like(h)

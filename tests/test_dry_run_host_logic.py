@@ -1,5 +1,5 @@
-"""CPU: walk the host-side sequencing of both renderers with NERO_DRY_RUN=1 (every kernel launch becomes a symbol lookup
-plus argument / shape assertions; tensors stay on the CPU).  Catches broken call sequences, buffer-shape mistakes and API
+"""CPU: walk the host-side sequencing of both renderers with tests/dry_run_harness.py installed (every kernel launch
+becomes a symbol lookup plus argument / shape assertions; tensors stay on the CPU).  Catches broken call sequences, buffer-shape mistakes and API
 regressions of the Python layer without a GPU; numerical results are meaningless in this mode and are not checked."""
 import os
 import subprocess
@@ -14,7 +14,8 @@ SCRIPT = textwrap.dedent('''
     import numpy as np, torch
     import nero_oracle as O, nero_oracle_mat as OM
     from nero_b200 import ops
-    assert ops.DRY_RUN
+    import dry_run_harness
+    fake = dry_run_harness.install()
     from nero_b200.renderer import NeROShapeRenderer, name2renderer
     from nero_b200.material import NeROMaterialRenderer
     assert set(name2renderer) == {'shape', 'material'}
@@ -72,12 +73,12 @@ SCRIPT = textwrap.dedent('''
     opt.step(); opt.zero_grad()
     sd = opt.state_dict()
     assert len(sd['state']) == len(list(m.parameters())) and sd['param_groups'][0]['lr'] == 1e-3
+    assert fake.calls > 1000
     print('DRY RUN OK')
 ''') % (ROOT, ROOT, ROOT)
 
 
 def test_host_logic_walks_end_to_end_in_dry_run_mode():
-    env = dict(os.environ, NERO_DRY_RUN='1')
-    env.pop('NERO_DEBUG_GEMM', None)
+    env = dict(os.environ)
     r = subprocess.run([sys.executable, '-c', SCRIPT], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'DRY RUN OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

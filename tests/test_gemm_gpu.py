@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import act_ref, dact_ref
+
 pytestmark = pytest.mark.gpu
 
 
@@ -38,7 +40,7 @@ def test_linear_bias_act(M, K, N, act):
     ops.linear(ops.Mat(A), L, ops.Mat(out, 4), N, act=act, act_param=0.0, m_cap=M)
     torch.cuda.synchronize()
     acc = A[:M, :K].double() @ W.t() + b
-    want = ops._act(acc, act, 0.0)
+    want = act_ref(acc, act, 0.0)
     scale = A[:M, :K].double().abs() @ W.abs().t() + b.abs()
     rel, ab = _err(out[:M, 4:4 + N], want, scale)
     print(f'linear M={M} K={K} N={N} act={act}: rel {rel:.2e} abs {ab:.2e}')
@@ -77,7 +79,7 @@ def test_linear_transposed_modes():
     out2 = torch.zeros(M, 256, device=dev)
     tail = torch.zeros(M, 64, device=dev)
     acc = dY[:, :N].double() @ W            # [M, 256]
-    s = ops._dact(H.double() * 1.4142135, 1)
+    s = dact_ref(H.double() * 1.4142135, 1)
     scale = dY[:, :N].double().abs() @ W.abs()
     # MUL_DACT with addend, tail split at 217
     ops.linear(ops.Mat(dY), L, ops.Mat(out), 256, transposed=True, mode=ops.EPI_MUL_DACT, oscale=0.70710678, H=ops.Mat(H),
@@ -92,7 +94,7 @@ def test_linear_transposed_modes():
     ops.linear(ops.Mat(dY), L, ops.Mat(out), 256, transposed=True, mode=ops.EPI_TANGENT, H=ops.Mat(H), hscale=1.0, dact=1,
                V=ops.Mat(V), out2=ops.Mat(out2))
     torch.cuda.synchronize()
-    s1 = ops._dact(H.double(), 1)
+    s1 = dact_ref(H.double(), 1)
     rel1, _ = _err(out, s1 * acc, scale + 1e-3)
     rel2, _ = _err(out2, 100 * (1 - s1) * V.double() * acc, 100 * V.double().abs() * scale + 1e-3)
     print(f'tangent rel {rel1:.2e} {rel2:.2e}')
@@ -172,10 +174,10 @@ def test_chain_matches_layerwise_and_fp64(M):
                         CL(L0, ops.EK_DACT_NONE, 39, transposed=True, save=Mat(U0))])
     torch.cuda.synchronize()
     acc2 = G.double() @ W2
-    s2 = ops._dact(H2.double()[:, :217] * 1.41421356, 1)
+    s2 = dact_ref(H2.double()[:, :217] * 1.41421356, 1)
     g2 = 0.70710678 * s2 * acc2[:, :217]
     tl = 0.70710678 * acc2[:, 217:]
-    g1 = ops._dact(H1.double(), 1) * (g2 @ W1) + add.double()
+    g1 = dact_ref(H1.double(), 1) * (g2 @ W1) + add.double()
     g0 = g1 @ W0
     for nm, got, want in [('g2', V2[:, :217], g2), ('tail', TL[:, :39], tl), ('g1', V1, g1), ('g0', U0[:, :39], g0)]:
         e = float((got.double() - want).abs().max())
@@ -207,15 +209,15 @@ def test_tangent_chain_matches_fp64(M):
                            out2=Mat(AB[1]), save=Mat(UB[1]), csrc=Mat(UB[1])),
                         CL(L2, ops.EK_TANGENT, 256, use_bias=False, H=Mat(H[2]), V=Mat(V[2]), out2=Mat(AB[2]), save=Mat(UB[2]))])
     torch.cuda.synchronize()
-    s0 = ops._dact(H[0].double(), 1)
+    s0 = dact_ref(H[0].double(), 1)
     a0 = U0[:, :39].double() @ W0.t()
     u1 = s0 * a0
     q0 = 100 * (1 - s0) * V[0].double() * a0
-    s1 = ops._dact(H[1].double()[:, :217] * 1.41421356, 1)
+    s1 = dact_ref(H[1].double()[:, :217] * 1.41421356, 1)
     a1 = u1 @ W1.t()
     u2 = torch.cat([0.70710678 * s1 * a1, skip.double()], -1)
     q1 = 100 * (1 - s1) * V[1].double()[:, :217] * a1
-    s2 = ops._dact(H[2].double(), 1)
+    s2 = dact_ref(H[2].double(), 1)
     a2 = u2 @ W2.t()
     u3 = s2 * a2
     q2 = 100 * (1 - s2) * V[2].double() * a2

@@ -39,7 +39,6 @@ def main():
     from nero_b200 import synthetic as SY
     from nero_b200 import ops, params as PR
     from nero_b200.material import NeROMaterialRenderer
-    assert not ops.DEBUG_GEMM and not ops.DRY_RUN
     dev = torch.device('cuda', 0)
     verts, tris = SY.test_scene(5)
     t0 = time.time()
