@@ -162,7 +162,11 @@ class Workload:
     def eik_weight(self):
         # gradient_error is a mean over the data-dependent number of inner samples: W*N_in/sum(N_in) makes the average of
         # the per-rank means equal the mean over all samples of the global batch (one scalar all-reduce, no host sync)
-        return self.dp.global_mean_weight(self.net.engine.state['N_in'], self.world) if self.world > 1 else 1.0
+        if self.world == 1:
+            return 1.0
+        e = self.net.engine
+        n = e.state['N_in'] if e.state['N_in'] is not None else e.w['n_in']      # graph mode keeps the count on the device
+        return self.dp.global_mean_weight(n, self.world)
 
     def resident_step(self):
         net, r, R = self.net, self.r, self.R
@@ -238,14 +242,24 @@ def run_ours(args):
     launches = (ops.launch_count - l0) // args.steps
     n_in, n_out, p_occ = wl.counts()
 
-    # ---- end to end through the public API with host buffers (H2D of the ray batch + D2H of the loss every step)
-    wl.net.cfg['train_ray_num'] = R
+    # ---- end to end through the public API with host buffers (H2D of the ray batch + D2H of the loss every step):
+    # the headline leg replays the step from CUDA graphs (cfg['cuda_graph']); the eager leg and the reference's default
+    # train_ray_num = 512 (where the step is launch-bound without graphs) are reported beside it
     n_e2e_warm = max(3, args.warmup // 2)
-    h2d = synthetic_dataset(wl.net, wl.host_rays, n_batches=args.steps + n_e2e_warm + 2)
-    for _ in range(n_e2e_warm):
-        wl.e2e_step(STEP)
-    ms_e2e = timed(lambda i: wl.e2e_step(STEP), args.steps, barrier)
-    n_in_e2e = wl.net.engine.state['N_in']
+
+    def e2e_leg(rays_n, graphed):
+        wl.net.cfg['train_ray_num'] = rays_n
+        wl.net.cfg['cuda_graph'] = graphed
+        h2d = synthetic_dataset(wl.net, {k: v[:rays_n].contiguous() for k, v in wl.host_rays.items()}, n_batches=args.steps + n_e2e_warm + 2)
+        for _ in range(n_e2e_warm):
+            wl.e2e_step(STEP)
+        ms_leg = timed(lambda i: wl.e2e_step(STEP), args.steps, barrier)
+        return ms_leg, h2d, int(wl.net.engine.w['n_in'].item())
+    ms_e2e_eager, h2d, _ = e2e_leg(R, False)
+    ms_e2e, h2d, n_in_e2e = e2e_leg(R, True)
+    r_small = min(512, R)
+    ms_small_eager, h2d_small, _ = e2e_leg(r_small, False)
+    ms_small, _, n_in_small = e2e_leg(r_small, True)
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
@@ -269,7 +283,7 @@ def run_ours(args):
                  'config': workload_config(True, wb.R, world), 'counts': {'n_in': nb_in, 'n_out': nb_out, 'p_occ': pb},
                  'step_tensor_tflops': algorithmic_flops(wb.R, nb_in, nb_out, pb, True) / (ms_b * 1e-3) / 1e12}
         del wb
-    ms, ms_e2e = reduce_max([ms, ms_e2e])
+    ms, ms_e2e, ms_e2e_eager, ms_small, ms_small_eager = reduce_max([ms, ms_e2e, ms_e2e_eager, ms_small, ms_small_eager])
     if rank == 0:
         peak_tf, peak_bw, which = measured_peaks()
         F = algorithmic_flops(R, n_in, n_out, p_occ, human=bear)
@@ -280,8 +294,13 @@ def run_ours(args):
             'config': workload_config(bear, R, world),
             'counts': {'n_in': n_in, 'n_out': n_out, 'p_occ': p_occ},
             'e2e': {'value': R * world / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': 4, 'n_in': n_in_e2e,
-                    'note': 'same rays as `value`, fetched from the pinned host ray table through net({"step"}) + loss read-back'},
+                    'd2h_bytes_per_step': 4, 'n_in': n_in_e2e, 'cuda_graph': True,
+                    'eager': {'value': R * world / (ms_e2e_eager * 1e-3), 'ms_per_step': ms_e2e_eager},
+                    'train_ray_num_512': {'rays_per_gpu': r_small, 'value': r_small * world / (ms_small * 1e-3), 'ms_per_step': ms_small,
+                                          'h2d_bytes_per_step': h2d_small, 'n_in': n_in_small,
+                                          'eager': {'value': r_small * world / (ms_small_eager * 1e-3), 'ms_per_step': ms_small_eager}},
+                    'note': 'same rays as `value`, fetched from the pinned host ray table through net({"step"}) + loss read-back; '
+                            'cfg cuda_graph replays the step from two captured graphs (no host sync inside the step)'},
             'gpu_launches': int(launches),
             'clocks': sampler.result(),
             'step_tensor_tflops': F / (ms * 1e-3) / 1e12,

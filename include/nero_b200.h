@@ -134,9 +134,9 @@ int nero_pe_tangent(const float* X0, int ldx, const float* DG, float* UB0, int l
 
 /* ---- NeuS SDF -> alpha + eikonal term (compute_sdf_alpha, network/renderer.py:484-512, :574) ---------------- */
 int nero_sdf_alpha_fwd(const float* Y8, int ldy, int sdf_col, const float* G, const float* pts, const int* ray_in, const float* rays_d,
-                       const float* variance, float car, float* alpha, float* gerr, const int* m_ptr, int m_cap, void* stream);
+                       const float* variance, const float* car, float* alpha, float* gerr, const int* m_ptr, int m_cap, void* stream);
 int nero_sdf_alpha_bwd(const float* Y8, int ldy, int sdf_col, const float* G, const float* pts, const int* ray_in, const float* rays_d,
-                       const float* variance, float car, const float* dalpha, const float* dgerr, float* dY8, int lddy, float* DG,
+                       const float* variance, const float* car, const float* dalpha, const float* dgerr, float* dY8, int lddy, float* DG,
                        float* d_inv_s, const int* m_ptr, int m_cap, void* stream);
 
 /* ---- outer NeRF activations (compute_density_alpha, network/renderer.py:346-347, 514-520) ------------------- */

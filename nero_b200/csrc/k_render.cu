@@ -273,7 +273,7 @@ __device__ __forceinline__ float inv_s_of(const float* variance) {
 
 __global__ void sdf_alpha_fwd_kernel(const float* __restrict__ Y8, int ldy, int sdf_col, const float* __restrict__ G,
                                      const float* __restrict__ pts, const int* __restrict__ ray_in,
-                                     const float* __restrict__ rays_d, const float* variance, float car, float* alpha,
+                                     const float* __restrict__ rays_d, const float* variance, const float* car_p, float* alpha,
                                      float* gerr, const int* m_ptr, int m_cap) {
   const int M = load_count(m_ptr, m_cap);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,14 +284,14 @@ __global__ void sdf_alpha_fwd_kernel(const float* __restrict__ Y8, int ldy, int 
   for (int c = 0; c < 3; ++c) d[c] /= dn;
   const float4 g4 = *reinterpret_cast<const float4*>(G + size_t(i) * 4);
   const float g[3] = {g4.x, g4.y, g4.z};
-  const SdfAlphaOut o = sdf_alpha_fwd(Y8[size_t(i) * ldy + sdf_col], g, d, pts[size_t(i) * 4 + 3], inv_s_of(variance), car);
+  const SdfAlphaOut o = sdf_alpha_fwd(Y8[size_t(i) * ldy + sdf_col], g, d, pts[size_t(i) * 4 + 3], inv_s_of(variance), *car_p);
   alpha[i] = o.alpha;
   gerr[i] = o.grad_err;
 }
 
 __global__ void sdf_alpha_bwd_kernel(const float* __restrict__ Y8, int ldy, int sdf_col, const float* __restrict__ G,
                                      const float* __restrict__ pts, const int* __restrict__ ray_in,
-                                     const float* __restrict__ rays_d, const float* variance, float car,
+                                     const float* __restrict__ rays_d, const float* variance, const float* car_p,
                                      const float* __restrict__ dalpha, const float* __restrict__ dgerr, float* dY8, int lddy,
                                      float* DG, float* d_inv_s, const int* m_ptr, int m_cap) {
   const int M = load_count(m_ptr, m_cap);
@@ -307,7 +307,7 @@ __global__ void sdf_alpha_bwd_kernel(const float* __restrict__ Y8, int ldy, int 
     float4 dg4 = *reinterpret_cast<float4*>(DG + size_t(i) * 4);
     float dg[3] = {dg4.x, dg4.y, dg4.z};
     float dsdf;
-    dis = sdf_alpha_bwd(Y8[size_t(i) * ldy + sdf_col], g, d, pts[size_t(i) * 4 + 3], inv_s_of(variance), car, dalpha[i],
+    dis = sdf_alpha_bwd(Y8[size_t(i) * ldy + sdf_col], g, d, pts[size_t(i) * 4 + 3], inv_s_of(variance), *car_p, dalpha[i],
                         dgerr ? dgerr[i] : 0.0f, &dsdf, dg);
     dY8[size_t(i) * lddy + sdf_col] = dsdf;
     *reinterpret_cast<float4*>(DG + size_t(i) * 4) = make_float4(dg[0], dg[1], dg[2], 0.f);
@@ -474,14 +474,14 @@ int pe_tangent_launch(const float* X0, int ldx, const float* DG, float* UB0, int
   return NERO_OK;
 }
 int sdf_alpha_forward(const float* Y8, int ldy, int sdf_col, const float* G, const float* pts, const int* ray_in, const float* rays_d,
-                      const float* variance, float car, float* alpha, float* gerr, const int* m_ptr, int m_cap, cudaStream_t st) {
+                      const float* variance, const float* car, float* alpha, float* gerr, const int* m_ptr, int m_cap, cudaStream_t st) {
   if (m_cap <= 0) return NERO_OK;
   sdf_alpha_fwd_kernel<<<blocks_for(m_cap, 256), 256, 0, st>>>(Y8, ldy, sdf_col, G, pts, ray_in, rays_d, variance, car, alpha, gerr, m_ptr, m_cap);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }
 int sdf_alpha_backward(const float* Y8, int ldy, int sdf_col, const float* G, const float* pts, const int* ray_in, const float* rays_d,
-                       const float* variance, float car, const float* dalpha, const float* dgerr, float* dY8, int lddy, float* DG,
+                       const float* variance, const float* car, const float* dalpha, const float* dgerr, float* dY8, int lddy, float* DG,
                        float* d_inv_s, const int* m_ptr, int m_cap, cudaStream_t st) {
   if (m_cap <= 0) return NERO_OK;
   sdf_alpha_bwd_kernel<<<blocks_for(m_cap, 256), 256, 0, st>>>(Y8, ldy, sdf_col, G, pts, ray_in, rays_d, variance, car, dalpha, dgerr, dY8, lddy, DG, d_inv_s, m_ptr, m_cap);

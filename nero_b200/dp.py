@@ -23,7 +23,8 @@ def global_mean_weight(n_local, world, group=None):
     if world == 1:
         return 1.0
     dev = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
-    t = torch.tensor([float(n_local)], device=dev)
+    # n_local may be the engine's device-side count (graph mode: it is never read back to the host)
+    t = n_local.detach().reshape(1).to(dev, torch.float32) if torch.is_tensor(n_local) else torch.tensor([float(n_local)], device=dev)
     tot = t.clone()
     dist.all_reduce(tot, group=group)
     return (world * t / torch.clamp(tot, min=1.0))[0]

@@ -85,23 +85,39 @@ def _fg_lookup_torch(lut, uv):
 
 
 class Grads:
-    """Maps parameters to their .grad buffers; missing grads become views of ONE flat zeroed buffer (the buffer a
-    data-parallel run all-reduces with a single NCCL call)."""
+    """Maps parameters to their .grad buffers: views of ONE persistent flat buffer (the buffer a data-parallel run
+    all-reduces with a single NCCL call, and whose addresses a captured CUDA graph of the backward pass can rely on).
+    A parameter whose .grad is None (after zero_grad(set_to_none=True)) gets its zeroed view back; a .grad somebody else
+    allocated is left alone unless `strict` (graph replay), where it is moved into the flat buffer."""
 
     def __init__(self, params):
         self.params = [p for p in params]
         self.total = sum(p.numel() for p in self.params)
         self.flat = None
+        self.views = None
 
-    def ensure(self):
-        if any(p.grad is None for p in self.params):
+    def ensure(self, strict=False):
+        if self.flat is None:
             self.flat = torch.zeros(self.total, dtype=torch.float32, device=self.params[0].device)
             off = 0
+            self.views = []
             for p in self.params:
                 n = p.numel()
-                if p.grad is None:
-                    p.grad = self.flat[off:off + n].view_as(p)
+                self.views.append(self.flat[off:off + n].view_as(p))
                 off += n
+        missing = [i for i, p in enumerate(self.params) if p.grad is None]
+        if len(missing) == len(self.params):
+            self.flat.zero_()
+        else:
+            for i in missing:
+                self.views[i].zero_()
+        for i in missing:
+            self.params[i].grad = self.views[i]
+        if strict:
+            for p, v in zip(self.params, self.views):
+                if p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                    p.grad = v
         return self.flat
 
 
@@ -514,6 +530,8 @@ class ShapeEngine:
         self.t_bg_hi = torch.cat([mids, zo[-1:]]).to(dev)
         self.t_lin64 = torch.linspace(0, 1, 64).to(dev)
         self.prepared_version = None
+        self.car_dev = torch.zeros(1, device=dev)      # cos_anneal_ratio: read by the kernels through a pointer, so a
+                                                       # captured graph of the step sees each step's value
 
     # ------------------------------------------------------------------ weights
     def predictors(self):
@@ -649,12 +667,17 @@ class ShapeEngine:
         return z_vals
 
     # ------------------------------------------------------------------ render_core forward (renderer.py:550-606)
-    def render_core_forward(self, rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio, step, perm=None):
+    def render_core_forward(self, rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio, step, perm=None, static=None):
+        """`static` (graph.TrainStepGraphs) selects the sync-free form used under CUDA-graph capture: no count is read back
+        to the host -- every kernel takes the device-side row count, the occlusion subset is drawn on the device, and
+        `cos_anneal_ratio` is whatever the caller put into `car_dev` -- and only `rgb` is returned."""
         cfg = self.cfg
         R, S = z_vals.shape
         self._alloc(R, S)
         w = self.w
         cap = R * S
+        if static is None:
+            self.car_dev.fill_(float(cos_anneal_ratio))
         var = self.p.deviation_network.variance.detach()
         K('nero_ray_prepare', rays_o, rays_d, z_vals, R, S, w['cnt_in'], w['cnt_out'], w['off_in'], w['off_out'], w['n_in'], w['n_out'])
         K('nero_ray_fill', rays_o, rays_d, z_vals, R, S, w['off_in'], w['off_out'], w['slot'], w['PTS'], w['RAY_IN'],
@@ -663,7 +686,7 @@ class ShapeEngine:
         # ---- inner samples: SDF value + analytic gradient
         self.sdf.forward_with_gradient(w, n_in, cap)
         self._shade_forward(rays_d, human_poses, n_in, cap)
-        K('nero_sdf_alpha_fwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, float(cos_anneal_ratio), w['ALPHA_IN'],
+        K('nero_sdf_alpha_fwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, self.car_dev, w['ALPHA_IN'],
           w['GERR'], n_in, cap)
         # ---- outer samples: NeRF++
         self.nerf.forward(w, n_out, cap)
@@ -678,6 +701,12 @@ class ShapeEngine:
             K('nero_occ_select', w['PTS'], w['Y8'], Y8_LD, Y8_SDF, w['G'], w['RAY_IN'], rays_d, float(cfg['occ_sdf_thresh']), n_in, cap,
               w['SEL'], w['OCC_COUNT'])
         with_reg = step < 1000
+        if static is not None:
+            assert not with_reg, 'the SDF-initialisation phase (step < 1000) runs eagerly'
+            P = self._occ_forward_static(static) if occ_on else 0
+            self.n_reg = 0
+            self.state = dict(R=R, S=S, N_in=None, P=P, rays_d=rays_d, hp=self._hp, step=step)
+            return rgb
         if with_reg:
             self.reg_forward(rays_o, rays_d, z_vals)
             w = self.w
@@ -686,7 +715,7 @@ class ShapeEngine:
         self.n_reg = counts[2] if with_reg else 0
         if occ_on:
             P = self._occ_forward(counts[1], perm)
-        self.state = dict(R=R, S=S, N_in=N_in, P=P, rays_d=rays_d, hp=self._hp, car=float(cos_anneal_ratio), step=step)
+        self.state = dict(R=R, S=S, N_in=N_in, P=P, rays_d=rays_d, hp=self._hp, step=step)
         return rgb, N_in, P
 
     def _occ_forward(self, cnt, perm):
@@ -702,9 +731,28 @@ class ShapeEngine:
             sel = torch.sort(sel[:cnt])[0][idx[:maxp].to(self.dev)].contiguous()
             cnt = maxp
             w['SEL_SUB'] = sel
-        P = cnt
+        return self._occ_march(sel, None, cnt)
+
+    def _occ_forward_static(self, static):
+        """The same uniform subset without a host-side count: every candidate draws a key, the `occ_loss_max_pn` smallest keys
+        win (a uniformly random subset, like randperm(cnt)[:max_pn]); the number of winners stays on the device and bounds
+        the occlusion kernels through their row-count pointer."""
+        w = self.w
+        maxp = self.cfg['occ_loss_max_pn']
+        cnt = w['OCC_COUNT']
+        keys = torch.where(static.ar < cnt, static.occ_keys, 2.0)
+        maxp = min(maxp, keys.shape[0])
+        vals, idx = torch.topk(keys, maxp, largest=False)
+        static.P_dev = (vals < 1.5).sum(dtype=torch.int32).reshape(1)
+        sel = w['SEL'][idx].contiguous()
+        return self._occ_march(sel, static.P_dev, maxp)
+
+    def _occ_march(self, sel, p_ptr, P):
+        """get_intersection / occlusion ground truth of the selected samples (renderer.py:514-548) and the L1 occlusion loss.
+        p_ptr: optional device count (<= P) bounding the rows that are initialised and that enter the loss."""
+        w = self.w
         var = self.p.deviation_network.variance.detach()
-        K('nero_occ_init', w['PTS'], w['REFL'], sel, None, P, 64, self.t_lin64, w['OCC_O'], w['OCC_D'], w['OCC_Z'], 64, w['SX0'], 64,
+        K('nero_occ_init', w['PTS'], w['REFL'], sel, p_ptr, P, 64, self.t_lin64, w['OCC_O'], w['OCC_D'], w['OCC_Z'], 64, w['SX0'], 64,
           w['SC'], 256)
         self.sdf.sdf_only(w['SX0'], w['SA'], w['SB'], w['SC'], w['SSDF'], None, P * 64)
         K('nero_upsample', w['OCC_O'], w['OCC_D'], P, w['OCC_Z'], 64, w['SSDF'], 64, 64, 16, var, 3.0e38, 1, 1, w['OCC_NEWZ'], 16,
@@ -714,7 +762,7 @@ class ShapeEngine:
           w['OCC_GT'])
         w['OCC_LOSS'].zero_()
         w['DOCC'].zero_()
-        K('nero_occ_loss', w['OCCP'], w['OCC_GT'], sel, None, P, w['OCC_LOSS'], w['DOCC'])
+        K('nero_occ_loss', w['OCCP'], w['OCC_GT'], sel, p_ptr, P, w['OCC_LOSS'], w['DOCC'])
         self.occ_sel = sel
         return P
 
@@ -859,11 +907,13 @@ class ShapeEngine:
         return out
 
     # ------------------------------------------------------------------ render_core backward
-    def render_core_backward(self, d_rgb, d_gerr, d_occ_scale):
+    def render_core_backward(self, d_rgb, d_gerr, d_occ_scale, static=None):
         """d_rgb [R,3]; d_gerr [N_in] or None; d_occ_scale: float tensor [] = dL/d(loss_occ) / P or None.
-        Accumulates into the .grad of every parameter."""
+        Accumulates into the .grad of every parameter.  Under graph capture (`static`) the caller has already made the .grad
+        buffers the views of the persistent flat buffer."""
         self._alloc_backward()
-        self.grads.ensure()
+        if static is None:
+            self.grads.ensure()
         st, w, cfg = self.state, self.w, self.cfg
         R, S, cap = st['R'], st['S'], st['R'] * st['S']
         rays_d = st['rays_d']
@@ -901,7 +951,7 @@ class ShapeEngine:
         # ---- SDF -> alpha
         w['D_INV_S'].zero_()
         dg = None if d_gerr is None else d_gerr.contiguous()
-        K('nero_sdf_alpha_bwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, st['car'], w['dALPHA_IN'], dg,
+        K('nero_sdf_alpha_bwd', w['Y8'], Y8_LD, Y8_SDF, w['G'], w['PTS'], w['RAY_IN'], rays_d, var, self.car_dev, w['dALPHA_IN'], dg,
           w['dY8'], Y8_LD, w['DG'], w['D_INV_S'], n_in, cap)
         frozen = cfg['freeze_inv_s_step'] is not None and st['step'] < cfg['freeze_inv_s_step']
         if not frozen:

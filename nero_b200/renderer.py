@@ -53,6 +53,8 @@ class NeROShapeRenderer(nn.Module):
         'test_downsample_ratio': True, 'downsample_ratio': 0.25, 'val_geometry': False,
         'rgb_loss': 'charbonier', 'apply_occ_loss': True, 'occ_loss_step': 20000, 'occ_loss_max_pn': 2048, 'occ_sdf_thresh': 0.01,
         'fixed_camera': False,
+        # not a reference key: replay train_step as two captured CUDA graphs (nero_b200/graph.py) once step >= 1000
+        'cuda_graph': False,
     }
 
     def __init__(self, cfg, training=True):
@@ -243,14 +245,51 @@ class NeROShapeRenderer(nn.Module):
         near, far = self.near_far_from_sphere(rays_o, rays_d)
         return rays_o, rays_d, near, far, self.get_human_coordinate_poses(poses)[idxs]
 
+    def _poses_on_device(self, dev):
+        p = getattr(self, '_train_poses_dev', None)
+        if p is None or p[0] is not self.train_poses or p[1].device != dev:
+            p = self._train_poses_dev = (self.train_poses, self.train_poses.to(dev))
+        return p[1]
+
+    def _train_step_graphed(self, step):
+        """train_step with the render replayed from CUDA graphs: no host<->device synchronisation anywhere in the step."""
+        from .graph import TrainStepGraphs
+        rn = self.cfg['train_ray_num']
+        dev = self.deviation_network.variance.device
+        sl = slice(self.train_batch_i, self.train_batch_i + rn)
+        dirs, idxs = self.train_batch['dirs'][sl], self.train_batch['idxs'][sl]
+        rgbs = self.train_batch['rgbs'][sl].to(dev, non_blocking=True)
+        key = TrainStepGraphs.key(self, rn, step)
+        graphs = self.__dict__.setdefault('_graphs', {})
+        g = graphs.get(key)
+        if g is None:
+            for k in [k for k in graphs if k[3] != key[3]]:      # workspaces were re-allocated: those graphs are stale
+                del graphs[k]
+            g = graphs[key] = TrainStepGraphs(self, rn, step)
+        rgb, gmean, locc = g.run(dirs, idxs, self._poses_on_device(dev), self.get_anneal_val(step), list(self.parameters()))
+        self.train_batch_i += rn
+        if self.train_batch_i + rn >= self.tbn:
+            self._shuffle_train_batch()
+        outputs = {'ray_rgb': rgb, 'gradient_error': gmean}
+        inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)
+        if self.cfg['freeze_inv_s_step'] is not None and step < self.cfg['freeze_inv_s_step']:
+            inv_s = inv_s.detach()
+        outputs['std'] = torch.mean(1 / inv_s)
+        if self.cfg['apply_occ_loss']:
+            outputs['loss_occ'] = locc
+        outputs['loss_rgb'] = self.compute_rgb_loss(rgb, rgbs)
+        return outputs
+
     def train_step(self, step):
+        if self.cfg['cuda_graph'] and step >= 1000:
+            return self._train_step_graphed(step)
         rn = self.cfg['train_ray_num']
         dev = self.deviation_network.variance.device
         batch = {k: v[self.train_batch_i:self.train_batch_i + rn].to(dev, non_blocking=True) for k, v in self.train_batch.items()}
         self.train_batch_i += rn
         if self.train_batch_i + rn >= self.tbn:
             self._shuffle_train_batch()
-        rays_o, rays_d, near, far, hp = self._process_ray_batch(batch, self.train_poses.to(dev))
+        rays_o, rays_d, near, far, hp = self._process_ray_batch(batch, self._poses_on_device(dev))
         outputs = self.render(rays_o, rays_d, near, far, hp, -1, self.get_anneal_val(step), is_train=True, step=step)
         outputs['loss_rgb'] = self.compute_rgb_loss(outputs['ray_rgb'], batch['rgbs'])
         return outputs

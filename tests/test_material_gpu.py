@@ -147,3 +147,40 @@ def test_material_image_render_and_vertex_materials():
     np.testing.assert_allclose(pm['metallic'], m_.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(pm['roughness'], torch.sqrt(torch.clamp(r_, min=1e-7)).numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(pm['albedo'], a_.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_construct_ray_batch_traces_every_pixel_like_the_reference_glue():
+    """NeROMaterialRenderer._construct_ray_batch (network/renderer.py:756-802): the init-time primary tracing of every pixel
+    of every image through the CUDA BVH -- camera rays from K / pose, hit filtering, per-ray capturer poses -- against the
+    same glue evaluated with the exhaustive tracer, in train (hit rays only) and eval (one image, hit mask) layout."""
+    net, g, cfg, steps, (verts, tris) = make_net('material_bell_p24')
+    n_img, h, w = 3, 20, 16
+    rays = O.synthetic_rays(n_img, seed=9)
+    info = {'imgs': torch.rand(n_img, 3, h, w), 'Ks': torch.tensor([[1.2 * w, 0, w / 2], [0, 1.2 * w, h / 2], [0, 0, 1.0]]).repeat(n_img, 1, 1),
+            'poses': rays['poses']}
+    tb = net._construct_ray_batch(info)
+    # the reference glue on the CPU with the exhaustive tracer
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
+    coords = torch.cat([torch.stack([xs, ys], -1).float().reshape(1, h * w, 2).repeat(n_img, 1, 1) + 0.5, torch.ones(n_img, h * w, 1)], 2)
+    rd = coords @ torch.inverse(info['Ks']).permute(0, 2, 1)
+    R, tt = info['poses'][:, :, :3], info['poses'][:, :, 3:]
+    rd = torch.nn.functional.normalize(rd @ R, dim=-1)
+    ro = (-R.permute(0, 2, 1) @ tt).permute(0, 2, 1).repeat(1, h * w, 1)
+    inters, normals, depth, hit = OM.renderer_trace(verts, tris, ro.reshape(-1, 3), rd.reshape(-1, 3))
+    hit = hit[:, 0]
+    assert 0.05 < hit.float().mean() < 0.95
+    n_hit = int(hit.sum())
+    assert abs(tb['rays_o'].shape[0] - n_hit) <= max(2, n_hit // 200), (tb['rays_o'].shape[0], n_hit)     # silhouette pixels may flip
+    if tb['rays_o'].shape[0] == n_hit:
+        allclose(tb['rays_d'], rd.reshape(-1, 3)[hit], 1e-6, 1e-6, 'rays_d')
+        allclose(tb['rays_o'], ro.reshape(-1, 3)[hit], 1e-6, 1e-6, 'rays_o')
+        d = (tb['inters'].cpu() - inters[hit]).abs().max(-1)[0]
+        assert float((d < 1e-4).float().mean()) > 0.995
+        allclose(tb['rgb'], info['imgs'].reshape(n_img, 3, h * w).permute(0, 2, 1).reshape(-1, 3)[hit], 0, 0, 'rgb')
+        hp = net.get_human_coordinate_poses(info['poses']).unsqueeze(1).repeat(1, h * w, 1, 1).reshape(-1, 3, 4)[hit]
+        allclose(tb['human_poses'], hp, 1e-6, 1e-6, 'human_poses')
+    one = {k: v[:1] for k, v in info.items()}
+    eb = net._construct_ray_batch(one, 'cpu', False)
+    assert eb['hit_mask'].shape == (h * w,) and eb['rays_o'].shape == (h * w, 3)
+    agree = (eb['hit_mask'].cpu() == hit[:h * w]).float().mean()
+    assert agree > 0.99, agree
