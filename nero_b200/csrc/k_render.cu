@@ -8,6 +8,7 @@
 //   composite fwd/bwd  : alpha compositing w = a * cumprod(1 - a + 1e-7), rgb = sum w c (renderer.py:578-579)
 #include "common.cuh"
 #include "math_shade.cuh"
+#include "tile_io.cuh"
 
 namespace nero {
 
@@ -93,10 +94,16 @@ struct FillParams {
   float* dist_out; int* ray_out;   // [cap_out]
 };
 
-__global__ void ray_fill_kernel(const FillParams q) {
+// one warp per ray; the encoded rows are staged per warp (tile_io.cuh): within a 32-sample step the inner samples of the warp
+// are consecutive rows of the compacted inner matrices (and likewise the outer ones), so each group is stored as whole rows
+constexpr int kFillLd = 85;          // PE10 of 4 coordinates = 84 columns, + 1
+constexpr int kFillWarps = 4;
+__global__ void __launch_bounds__(kFillWarps * 32) ray_fill_kernel(const FillParams q) {
+  __shared__ float s_tile[kFillWarps][32][kFillLd];
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= q.R) return;
+  float (*tile)[kFillLd] = s_tile[threadIdx.x >> 5];
   const int S = q.S;
   const float o[3] = {q.rays_o[r * 3], q.rays_o[r * 3 + 1], q.rays_o[r * 3 + 2]};
   const float d[3] = {q.rays_d[r * 3], q.rays_d[r * 3 + 1], q.rays_d[r * 3 + 2]};
@@ -113,39 +120,44 @@ __global__ void ray_fill_kernel(const FillParams q) {
     const unsigned bi = __ballot_sync(0xffffffffu, valid && inner);
     const unsigned bo = __ballot_sync(0xffffffffu, valid && !inner);
     const unsigned lt = (1u << lane) - 1u;
+    const int n_i = __popc(bi), n_o = __popc(bo);
+    const int rank = inner ? __popc(bi & lt) : __popc(bo & lt);
+    // ---- inner samples: rows [base_in, base_in + n_i)
     if (valid && inner) {
-      const int i = base_in + __popc(bi & lt);
+      const int i = base_in + rank;
       q.slot[size_t(r) * S + j] = i;
       *reinterpret_cast<float4*>(q.pts + size_t(i) * 4) = make_float4(p[0], p[1], p[2], dist);
       q.ray_in[i] = r;
-      float pe[39];
-      pe_encode<3>(p, 6, pe);
-      float* x0 = q.X0 + size_t(i) * q.ld_x0;
-      float* h4 = q.H4 + size_t(i) * q.ld_h4 + 217;
-      for (int c = 0; c < 39; ++c) { x0[c] = pe[c]; h4[c] = pe[c] * kInvSqrt2; }
+      pe_encode<3>(p, 6, tile[rank]);
       float* y8 = q.Y8 + size_t(i) * q.ld_y8 + 256;
       y8[0] = p[0]; y8[1] = p[1]; y8[2] = p[2];
-    } else if (valid) {
-      const int io = base_out + __popc(bo & lt);
+    }
+    if (n_i) {
+      warp_rows_store<kFillLd>(tile, q.X0 + size_t(base_in) * q.ld_x0, q.ld_x0, 39, n_i, lane);
+      warp_rows_store<kFillLd>(tile, q.H4 + size_t(base_in) * q.ld_h4 + 217, q.ld_h4, 39, n_i, lane, kInvSqrt2);
+    }
+    // ---- outer samples: rows [base_out, base_out + n_o)
+    if (valid && !inner) {
+      const int io = base_out + rank;
       q.slot[size_t(r) * S + j] = -1 - io;
       q.dist_out[io] = dist;
       q.ray_out[io] = r;
       // renderer.py:515-516: norm = |p| ; points = cat[p/norm, 1/norm]
       const float nrm = norm3_rn(p);
       const float p4[4] = {p[0] / nrm, p[1] / nrm, p[2] / nrm, 1.0f / nrm};
-      float pe[84];
-      pe_encode<4>(p4, 10, pe);
-      float* xn = q.XN + size_t(io) * q.ld_xn;
-      float* h5 = q.H5 + size_t(io) * q.ld_h5;
-      for (int c = 0; c < 84; ++c) { xn[c] = pe[c]; h5[c] = pe[c]; }
-      const float view[3] = {-d[0] / dn, -d[1] / dn, -d[2] / dn};   // -F.normalize(rays_d) (renderer.py:564,568)
-      float pv[27];
-      pe_encode<3>(view, 4, pv);
-      float* fv = q.FV + size_t(io) * q.ld_fv + 256;
-      for (int c = 0; c < 27; ++c) fv[c] = pv[c];
+      pe_encode<4>(p4, 10, tile[rank]);
     }
-    base_in += __popc(bi);
-    base_out += __popc(bo);
+    if (n_o) {
+      warp_rows_store<kFillLd>(tile, q.XN + size_t(base_out) * q.ld_xn, q.ld_xn, 84, n_o, lane);
+      warp_rows_store<kFillLd>(tile, q.H5 + size_t(base_out) * q.ld_h5, q.ld_h5, 84, n_o, lane);
+      if (valid && !inner) {
+        const float view[3] = {-d[0] / dn, -d[1] / dn, -d[2] / dn};   // -F.normalize(rays_d) (renderer.py:564,568)
+        pe_encode<3>(view, 4, tile[rank]);
+      }
+      warp_rows_store<kFillLd>(tile, q.FV + size_t(base_out) * q.ld_fv + 256, q.ld_fv, 27, n_o, lane);
+    }
+    base_in += n_i;
+    base_out += n_o;
   }
 }
 
@@ -219,6 +231,18 @@ __global__ void points_fill_kernel(const float* __restrict__ pts3, int N, float*
 __global__ void dact_times_row_kernel(const float* __restrict__ H, int ldh, const float* __restrict__ row, float* V, int ldv,
                                       int ncol, const int* m_ptr, int m_cap) {
   const int M = load_count(m_ptr, m_cap);
+  if (((ncol | ldh | ldv) & 3) == 0 && ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(V)) & 15) == 0) {   // float4 path (every caller: 256-wide rows)
+    const int q4 = ncol >> 2;
+    const unsigned total = unsigned(M) * unsigned(q4);
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+      const unsigned i = idx / unsigned(q4), j = (idx % unsigned(q4)) * 4u;
+      const float4 h = *reinterpret_cast<const float4*>(H + size_t(i) * ldh + j);
+      const float4 w = *reinterpret_cast<const float4*>(row + j);
+      *reinterpret_cast<float4*>(V + size_t(i) * ldv + j) =
+          make_float4(dsoftplus100_from_h(h.x) * w.x, dsoftplus100_from_h(h.y) * w.y, dsoftplus100_from_h(h.z) * w.z, dsoftplus100_from_h(h.w) * w.w);
+    }
+    return;
+  }
   const size_t total = size_t(M) * ncol;
   for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
     const int i = int(idx / ncol), j = int(idx % ncol);
@@ -242,28 +266,42 @@ __global__ void row_axpy_kernel(const float* __restrict__ a, int lda, const floa
 }
 
 // g = J_PE^T (U0 + USKIP)
-__global__ void pe_grad_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ U0, int ldu,
-                               const float* __restrict__ US, int lds, float* G, const int* m_ptr, int m_cap) {
+constexpr int kPeLd = 41;            // PE6 of 3 coordinates = 39 columns
+__global__ void __launch_bounds__(128) pe_grad_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ U0, int ldu,
+                                                      const float* __restrict__ US, int lds, float* G, const int* m_ptr, int m_cap) {
+  __shared__ float s_u[4][32][kPeLd], s_x[4][32][kPeLd];
   const int M = load_count(m_ptr, m_cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
-  float u[39], g[3];
-  for (int c = 0; c < 39; ++c) u[c] = U0[size_t(i) * ldu + c] + US[size_t(i) * lds + c];
-  pe_backward<3>(X0 + size_t(i) * ldx, 6, u, g);
-  *reinterpret_cast<float4*>(G + size_t(i) * 4) = make_float4(g[0], g[1], g[2], 0.f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = blockIdx.x * blockDim.x + warp * 32;
+  if (base >= M) return;
+  const int rows = min(32, M - base);
+  warp_rows_load<kPeLd>(s_u[warp], U0 + size_t(base) * ldu, ldu, US + size_t(base) * lds, lds, 39, rows, lane);
+  warp_rows_load<kPeLd>(s_x[warp], X0 + size_t(base) * ldx, ldx, nullptr, 0, 39, rows, lane);
+  if (lane >= rows) return;
+  float g[3];
+  pe_backward<3>(s_x[warp][lane], 6, s_u[warp][lane], g);
+  *reinterpret_cast<float4*>(G + size_t(base + lane) * 4) = make_float4(g[0], g[1], g[2], 0.f);
 }
 
 // ubar_0 = J_PE dg  -> UB0[:, 0:39];  UB4[:, 217:256] = ubar_0 / sqrt2
-__global__ void pe_tangent_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ DG, float* UB0, int ld0,
-                                  float* UB4, int ld4, const int* m_ptr, int m_cap) {
+__global__ void __launch_bounds__(128) pe_tangent_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ DG, float* UB0,
+                                                         int ld0, float* UB4, int ld4, const int* m_ptr, int m_cap) {
+  __shared__ float s_x[4][32][kPeLd];
   const int M = load_count(m_ptr, m_cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
-  const float4 dg4 = *reinterpret_cast<const float4*>(DG + size_t(i) * 4);
-  const float dg[3] = {dg4.x, dg4.y, dg4.z};
-  float t[39];
-  pe_tangent<3>(X0 + size_t(i) * ldx, 6, dg, t);
-  for (int c = 0; c < 39; ++c) { UB0[size_t(i) * ld0 + c] = t[c]; UB4[size_t(i) * ld4 + 217 + c] = t[c] * kInvSqrt2; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = blockIdx.x * blockDim.x + warp * 32;
+  if (base >= M) return;
+  const int rows = min(32, M - base);
+  warp_rows_load<kPeLd>(s_x[warp], X0 + size_t(base) * ldx, ldx, nullptr, 0, 39, rows, lane);
+  if (lane < rows) {
+    const float4 dg4 = *reinterpret_cast<const float4*>(DG + size_t(base + lane) * 4);
+    const float dg[3] = {dg4.x, dg4.y, dg4.z};
+    float t[39];
+    pe_tangent<3>(s_x[warp][lane], 6, dg, t);
+    for (int c = 0; c < 39; ++c) s_x[warp][lane][c] = t[c];
+  }
+  warp_rows_store<kPeLd>(s_x[warp], UB0 + size_t(base) * ld0, ld0, 39, rows, lane);
+  warp_rows_store<kPeLd>(s_x[warp], UB4 + size_t(base) * ld4 + 217, ld4, 39, rows, lane, kInvSqrt2);
 }
 
 // ------------------------------------------------------------------ SDF -> alpha

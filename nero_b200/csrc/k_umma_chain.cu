@@ -96,6 +96,13 @@ constexpr int kChThreads = (kChEpiWarps + 4) * 32;
 #define NERO_WSTAGES 4
 #endif
 constexpr int kWStages = NERO_WSTAGES;
+// Timing experiments only (tools/bench_chain.py A/B builds; results are WRONG with any bit set): 1|2 = the MMA issuer and the
+// epilogue ignore each other's barriers (each free-runs at its own speed), 4 = no MMA instructions are issued,
+// 8 = no epilogue math / aux traffic, 16 = only the hi plane of W is loaded (half the bytes).
+#ifndef NERO_CHAIN_EXP
+#define NERO_CHAIN_EXP 0
+#endif
+constexpr int kExp = NERO_CHAIN_EXP;
 constexpr uint32_t kWStageBytes = 2 * 128 * 128;   // hi + lo planes of up to 128 weight rows x 64 K (one N half of a K chunk)
 constexpr int kSlotsIn = NERO_SLOTS_IN, kSlotsOut = NERO_SLOTS_OUT;         // per team
 constexpr uint32_t kSlotBytes = CH_BM * 16 * 4;    // [128 rows x 16 fp32] = 8 KB
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
       const bool row_ok = rl < rows_valid;
       const bool tile_tma_ok = tile_tma_store_ok(p, tile, M);
       // ---- first A operand: fp32 rows from HBM -> split-bf16 in TMEM
-      for (int u = team; u < p.a0_units; u += kTeams) {
+      for (int u = team; u < ((kExp & 8) ? 0 : p.a0_units); u += kTeams) {
         float x[16];
         if (p.a0_tma) {
           slot_read16(in_wait(t), t.rowoff, t.sw, x);
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
           const int i = warp * 32 + lane;
           if (i < 256) sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
         }
-        mbar_wait(acc_ready, acc_phase);
+        if (!(kExp & 2)) mbar_wait(acc_ready, acc_phase);
         tcgen05_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(kChEpiWarps * 32));
         // The layer runs as two N halves (k_umma: half 0 = accumulator columns [0, h_units*16)): the units of half 0 are
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         const bool hand_over = l + 1 < p.n_layers;
         bool got_acc1 = false, got_free = false, lo_sent = false;
         auto before_unit = [&](int u) {
-          if (u >= h_units && !got_acc1) { mbar_wait(acc_ready + 1, acc_phase); tcgen05_fence_after(); got_acc1 = true; }
+          if (u >= h_units && !got_acc1) { if (!(kExp & 2)) mbar_wait(acc_ready + 1, acc_phase); tcgen05_fence_after(); got_acc1 = true; }
           if (u >= 8 && !lo_sent) {      // this warp's share of A columns K < 128 is complete (units ascend)
             tmem_st_wait();
             tcgen05_fence_before();
@@ -518,11 +525,12 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         // the next A operand (columns K < 128) is written over the one the half-1 MMAs of THIS layer still read: wait for
         // them right before the first such write (by then the unit's own math has covered most of that time)
         auto before_a_write = [&](int u) {
-          if (u < 8 && !got_acc1 && !got_free) { mbar_wait(a_free, acc_phase); tcgen05_fence_after(); got_free = true; }
+          if (u < 8 && !got_acc1 && !got_free) { if (!(kExp & 2)) mbar_wait(a_free, acc_phase); tcgen05_fence_after(); got_free = true; }
         };
         const int u0 = (team + l) % kTeams;          // rotate the unit -> team assignment so the 16 = 6+5+5 split evens out
 #define NERO_EPI_CALL(K) epi_layer<K>(p, l, t, u0, tl, tile, rows_valid, tile_tma_ok, sb, before_unit, before_a_write)
-        if constexpr (FAM == 0) {
+        if constexpr ((kExp & 8) != 0) {
+        } else if constexpr (FAM == 0) {
           if (L.kind == EK_BIAS_SOFTPLUS) NERO_EPI_CALL(EK_BIAS_SOFTPLUS);
           else if (L.kind == EK_BIAS_RELU) NERO_EPI_CALL(EK_BIAS_RELU);
           else NERO_EPI_CALL(EK_BIAS_GENERIC);
@@ -535,8 +543,8 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         }
 #undef NERO_EPI_CALL
         // every barrier of the layer is passed exactly once per thread (phase bookkeeping), all MMAs of the layer are done
-        if (!got_acc1) { mbar_wait(acc_ready + 1, acc_phase); tcgen05_fence_after(); }
-        if (!got_free) mbar_wait(a_free, acc_phase);
+        if (!got_acc1 && !(kExp & 2)) { mbar_wait(acc_ready + 1, acc_phase); tcgen05_fence_after(); }
+        if (!got_free && !(kExp & 2)) mbar_wait(a_free, acc_phase);
         acc_phase ^= 1;
         tmem_st_wait();
         tcgen05_fence_before();
@@ -564,13 +572,13 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         for (int hf = 0; hf < nh; ++hf) {
           const uint32_t d_col = tmem_base + kAccCol + uint32_t(hf) * half_rows;
           for (int c = 0; c < kc; ++c, ++g) {
-            if (hf == 0 && c == 0) { mbar_wait(a_ready, a_phase); tcgen05_fence_after(); }           // A columns K < 128, half 0 drained
+            if (hf == 0 && c == 0 && !(kExp & 1)) { mbar_wait(a_ready, a_phase); tcgen05_fence_after(); }           // A columns K < 128, half 0 drained
             // all of A written, half 1 drained.  Also required before this layer's a_free / acc_ready[1] commits are
             // issued: every epilogue thread passes the previous layer's phase of those barriers before it arrives on
             // a_ready[1], so waiting here keeps a barrier from completing two phases ahead of a waiter (single-half
             // layers would otherwise commit them after a_ready[0] alone).
             const bool commits_late = (hf == nh - 1) && (c == (kc < 2 ? kc : 2) - 1 || c == kc - 1);
-            if (!hi_ok && (c == 2 || hf == 1 || commits_late)) { mbar_wait(a_ready + 1, a_phase); tcgen05_fence_after(); hi_ok = true; }
+            if (!hi_ok && (c == 2 || hf == 1 || commits_late)) { if (!(kExp & 1)) mbar_wait(a_ready + 1, a_phase); tcgen05_fence_after(); hi_ok = true; }
             const int s = g % kWStages;
             mbar_wait(&full[s], (g / kWStages) & 1);
             tcgen05_fence_after();
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
               const uint32_t b_hi = smem_u32(s_w + s * kWStageBytes);
               const uint32_t b_lo = b_hi + b_plane;
 #pragma unroll
-              for (int k = 0; k < CH_BK / 16; ++k) {
+              for (int k = 0; k < ((kExp & 4) ? 0 : CH_BK / 16); ++k) {
                 const uint32_t a_col = uint32_t(c * 32 + k * 8);
                 const uint64_t dbh = make_desc_k_sw128(b_hi + k * 32), dbl = make_desc_k_sw128(b_lo + k * 32);
                 umma_bf16_ts(d_col, tmem_base + kALoCol + a_col, dbh, idesc, (c | k) != 0);
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
             __syncwarp();
           }
         }
-        if (!hi_ok) { mbar_wait(a_ready + 1, a_phase); tcgen05_fence_after(); }      // keep the phases in step
+        if (!hi_ok && !(kExp & 1)) { mbar_wait(a_ready + 1, a_phase); tcgen05_fence_after(); }      // keep the phases in step
         a_phase ^= 1;
       }
     }
@@ -615,9 +623,9 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
             if (elect_one()) {
               // rows [hf*half_rows, +half_rows) of the chunk's hi plane and of its lo plane
               const uint8_t* src = L.wimg + size_t(c) * 2u * plane + size_t(hf) * hp;
-              mbar_arrive_expect_tx(&full[s], 2u * hp);
+              mbar_arrive_expect_tx(&full[s], (kExp & 16) ? hp : 2u * hp);
               bulk_copy_g2s(s_w + s * kWStageBytes, src, hp, &full[s]);
-              bulk_copy_g2s(s_w + s * kWStageBytes + hp, src + plane, hp, &full[s]);
+              if (!(kExp & 16)) bulk_copy_g2s(s_w + s * kWStageBytes + hp, src + plane, hp, &full[s]);
             }
             __syncwarp();
           }
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     }
   } else if (warp == kChAuxWarp) {
     // ============================== aux loader: lane t fills the input FIFO of team t, as far ahead as slots are free
-    if (lane < kTeams) {
+    if (lane < kTeams && !(kExp & 8)) {
       const int tm = lane;
       uint64_t* fb = b_in_full + tm * kSlotsIn;
       uint64_t* eb = b_in_empty + tm * kSlotsIn;
@@ -661,7 +669,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     }
   } else {
     // ============================== store warp: lane t drains the output FIFO of team t with TMA stores
-    if (lane < kTeams) {
+    if (lane < kTeams && !(kExp & 8)) {
       const int tm = lane;
       uint64_t* fb = b_out_full + tm * kSlotsOut;
       uint64_t* eb = b_out_empty + tm * kSlotsOut;

@@ -96,15 +96,16 @@ int prep_weight(const float* v, const float* g, int K, int row0, int nrows, cons
   return NERO_OK;
 }
 
-// one block per layer row n = row0 + blockIdx.x; blockDim = (kcols, 4): the P split-K partials are summed by 4 thread
-// groups in parallel (the per-row reads are latency bound), then reduced through shared memory.
+// one block per layer row n = row0 + blockIdx.x; blockDim = (kcols, ny): the P split-K partials are summed by ny thread
+// groups in parallel (the per-row reads are latency bound), then reduced through shared memory ([ny][K] floats).
 __device__ __forceinline__ void wgrad_finish_row(int r, const float* __restrict__ partial, int P, int rows_partial, int ld_partial,
                                     const float* __restrict__ bias_partial, int K, int row0,
                                     const int* __restrict__ kmap, float in_scale, const float* __restrict__ v,
                                     const float* __restrict__ g, float* grad_w, float* grad_g, float* grad_b,
                                     const float* __restrict__ extra_row, float extra_scale) {
   __shared__ float sh[32];
-  extern __shared__ float s_dw[];  // [4][K] partial sums, then [K] in slot 0
+  extern __shared__ float s_dw[];  // [ny][K] partial sums, then [K] in slot 0
+  const int ny = blockDim.y;
   const int n = row0 + r;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
   const size_t pstride = size_t(rows_partial) * ld_partial;
@@ -113,17 +114,19 @@ __device__ __forceinline__ void wgrad_finish_row(int r, const float* __restrict_
     const float* pp = partial + size_t(r) * ld_partial + kc;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int pidx = threadIdx.y;
-    for (; pidx + 12 < P; pidx += 16) {
-      a0 += pp[size_t(pidx) * pstride]; a1 += pp[size_t(pidx + 4) * pstride];
-      a2 += pp[size_t(pidx + 8) * pstride]; a3 += pp[size_t(pidx + 12) * pstride];
+    for (; pidx + 3 * ny < P; pidx += 4 * ny) {
+      a0 += pp[size_t(pidx) * pstride]; a1 += pp[size_t(pidx + ny) * pstride];
+      a2 += pp[size_t(pidx + 2 * ny) * pstride]; a3 += pp[size_t(pidx + 3 * ny) * pstride];
     }
-    for (; pidx < P; pidx += 4) a0 += pp[size_t(pidx) * pstride];
+    for (; pidx < P; pidx += ny) a0 += pp[size_t(pidx) * pstride];
     s_dw[threadIdx.y * K + k] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   for (int k = tid; k < K; k += nthreads) {
     const int kc = kmap ? kmap[k] : k;
-    float acc = ((s_dw[k] + s_dw[K + k]) + (s_dw[2 * K + k] + s_dw[3 * K + k])) * in_scale;
+    float acc = s_dw[k];
+    for (int y = 1; y < ny; ++y) acc += s_dw[y * K + k];
+    acc *= in_scale;
     if (extra_row && r == 0) acc += extra_scale * extra_row[kc];
     s_dw[k] = acc;   // slot 0 (each k is read and written by the same thread)
   }
@@ -175,7 +178,9 @@ __global__ void wgrad_finish_batch_kernel(const FinishJob* __restrict__ jobs) {
 int wgrad_finish_batch(const void* jobs_dev, int n_jobs, int max_rows, int max_k, cudaStream_t stream) {
   if (n_jobs <= 0 || max_rows <= 0) return NERO_OK;
   if (!jobs_dev || max_k <= 0 || max_k > 1024) return NERO_ERR_ARG;
-  wgrad_finish_batch_kernel<<<dim3(max_rows, n_jobs), dim3(256, 4), 4 * max_k * sizeof(float), stream>>>(static_cast<const FinishJob*>(jobs_dev));
+  // the batched jobs come from the accumulating weight-gradient GEMM (one accumulator, P = 1): a row is ~1.5 KB of work, so
+  // small blocks (many resident per SM) instead of the (256, 4) layout of the split-K reduction
+  wgrad_finish_batch_kernel<<<dim3(max_rows, n_jobs), dim3(128, 1), max_k * sizeof(float), stream>>>(static_cast<const FinishJob*>(jobs_dev));
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }
@@ -199,27 +204,54 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int ncol, co
                               const int* __restrict__ m_ptr, int m_cap, float* out) {
   int M = m_ptr ? *m_ptr : m_cap;
   if (M > m_cap) M = m_cap;
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int rlane = threadIdx.x >> 5;           // 8 row lanes
+  // 256 threads = 8 row lanes x 32 column lanes of 4 adjacent columns each (one float4 per row and thread)
+  const int lane = threadIdx.x & 31, rlane = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + lane) * 4;
   const int rows_per_block = (M + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  float acc = 0.0f;
-  if (col < ncol)
-    for (int r = r0 + rlane; r < r1; r += 8) acc += (w ? w[size_t(r) * ldw] : 1.0f) * X[size_t(r) * ldx + col];
-  __shared__ float sh[8][33];
-  sh[rlane][threadIdx.x & 31] = acc;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && col + 3 < ncol;
+  if (vec) {
+    int r = r0 + rlane;
+    for (; r + 24 < r1; r += 32) {          // four independent row loads in flight
+      float4 x[4]; float s[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        x[u] = *reinterpret_cast<const float4*>(X + size_t(r + 8 * u) * ldx + col);
+        s[u] = w ? w[size_t(r + 8 * u) * ldw] : 1.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc[0] += s[u] * x[u].x; acc[1] += s[u] * x[u].y; acc[2] += s[u] * x[u].z; acc[3] += s[u] * x[u].w; }
+    }
+    for (; r < r1; r += 8) {
+      const float4 x = *reinterpret_cast<const float4*>(X + size_t(r) * ldx + col);
+      const float s = w ? w[size_t(r) * ldw] : 1.0f;
+      acc[0] += s * x.x; acc[1] += s * x.y; acc[2] += s * x.z; acc[3] += s * x.w;
+    }
+  } else {
+    for (int r = r0 + rlane; r < r1; r += 8) {
+      const float s = w ? w[size_t(r) * ldw] : 1.0f;
+      for (int c = 0; c < 4; ++c)
+        if (col + c < ncol) acc[c] += s * X[size_t(r) * ldx + col + c];
+    }
+  }
+  __shared__ float sh[8][32][5];
+  for (int c = 0; c < 4; ++c) sh[rlane][lane][c] = acc[c];
   __syncthreads();
-  if (rlane == 0 && col < ncol) {
-    float t = 0.0f;
-    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x & 31];
-    atomicAdd(out + col, t);
+  if (rlane == 0) {
+    for (int c = 0; c < 4; ++c) {
+      if (col + c >= ncol) break;
+      float t = 0.0f;
+      for (int i = 0; i < 8; ++i) t += sh[i][lane][c];
+      atomicAdd(out + col + c, t);
+    }
   }
 }
 
 int colsum(const float* X, int ldx, int ncol, const float* w, int ldw, const int* m_ptr, int m_cap, float* out,
            cudaStream_t stream) {
   if (m_cap <= 0 || ncol <= 0) return NERO_OK;
-  dim3 grid((ncol + 31) / 32, 64);
+  dim3 grid((ncol + 127) / 128, 148);
   colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, ncol, w, ldw, m_ptr, m_cap, out);
   NERO_LAUNCH_CHECK();
   return NERO_OK;

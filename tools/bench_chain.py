@@ -4,7 +4,7 @@ derivative sweep (H in, V out per layer) and the tangent sweep (H, V in; two out
 the algorithmic TFLOP/s (2*M*K*N per layer)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np, torch
 from nero_b200 import ops
 from nero_b200.ops import Mat, chain, chain_layer as CL
