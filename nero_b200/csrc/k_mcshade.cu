@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "math_enc.cuh"
 #include "math_shade.cuh"
+#include "tile_io.cuh"
 #include "math_mc.cuh"
 #include "../../include/nero_b200.h"
 
@@ -90,64 +91,85 @@ __global__ void mc_scan_kernel(const McParams q, int nblk, long N) {   // one bl
 
 // rows + encodings.  Outer row: IDE(dir, 0) [+ IDE(sphere point, 0)] and the human-light IPE; inner row: PE8(hit point) at
 // columns 0..50, IDE(reflection of -dir about the hit normal, 0) at 52..123 (field.py:814-820, 822-856).
-__global__ void mc_fill_kernel(const McParams q, long N) {
+// The compaction keeps ray order, so the misses of a warp are consecutive rows of the outer matrices and its hits consecutive
+// rows of the inner one: each group is staged in a per-warp tile and stored as whole rows (tile_io.cuh).  Per-thread 16-byte
+// stores into 32 different rows wrote 2.6x the algorithmic bytes to DRAM (half-filled sectors evicted from L2).
+constexpr int kMcTileLd = 73;
+constexpr int kMcFillSmem = (kClsBlock / 32) * 32 * kMcTileLd * 4;
+__global__ void __launch_bounds__(kClsBlock) mc_fill_kernel(const McParams q, long N) {
+  extern __shared__ float s_mc_tiles[];
   __shared__ int s_warp[kClsBlock / 32];
   const int S = q.Sd + q.Ss;
   const long i = long(blockIdx.x) * kClsBlock + threadIdx.x;
   const bool valid = i < N;
   const float4 nh = valid ? reinterpret_cast<const float4*>(q.nrm_hit)[i] : make_float4(0, 0, 0, 0);
-  const bool hit = valid && nh.w > 0.5f;
-  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  const bool hit = valid && nh.w > 0.5f, miss = valid && !hit;
+  const unsigned b = __ballot_sync(0xffffffffu, hit), bm = __ballot_sync(0xffffffffu, miss);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) s_warp[wid] = __popc(b);
   __syncthreads();
-  int before = q.blk_off[blockIdx.x];
-  for (int k = 0; k < wid; ++k) before += s_warp[k];
-  before += __popc(b & ((1u << lane) - 1u));
-  if (!valid) return;
-  const float4 d4 = *reinterpret_cast<const float4*>(q.dir + i * 4);
-  const float d[3] = {d4.x, d4.y, d4.z};
-  const int p = int(i / S);
-  float enc[72];
-  if (!hit) {
-    const long r = i - before;
-    q.slot[i] = int(r);
-    ide_forward(c_ide_mc, d, 0.f, enc);
-    float* eo = q.EO + r * q.ldeo;
-    for (int c = 0; c < 72; c += 4) *reinterpret_cast<float4*>(eo + c) = make_float4(enc[c], enc[c + 1], enc[c + 2], enc[c + 3]);
+  int wbefore = q.blk_off[blockIdx.x];                  // hits before this warp
+  for (int k = 0; k < wid; ++k) wbefore += s_warp[k];
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_hit = __popc(b), n_miss = __popc(bm);
+  const int rank = hit ? __popc(b & lt) : __popc(bm & lt);
+  const long row_i0 = wbefore;                          // first inner row of the warp
+  const long row_o0 = (i - lane) - wbefore;             // first outer row of the warp
+  float (*tile)[kMcTileLd] = reinterpret_cast<float (*)[kMcTileLd]>(s_mc_tiles + size_t(wid) * 32 * kMcTileLd);
+  float d[3] = {0.f, 0.f, 1.f};
+  int p = 0;
+  if (valid) {
+    const float4 d4 = *reinterpret_cast<const float4*>(q.dir + i * 4);
+    d[0] = d4.x; d[1] = d4.y; d[2] = d4.z;
+    p = int(i / S);
+  }
+  // ---- misses -> outer rows
+  if (n_miss) {
+    if (miss) {
+      q.slot[i] = int(row_o0 + rank);
+      ide_forward(c_ide_mc, d, 0.f, tile[rank]);
+    }
+    float* eo = q.EO + row_o0 * q.ldeo;
+    warp_rows_store4<kMcTileLd, 18>(tile, eo, q.ldeo, n_miss, lane);
     if (q.sphere_dir) {
-      float sp[3], pu[3];
-      mc_sphere_point(q.pts + 3 * p, d, sp, pu);
-      ide_forward(c_ide_mc, sp, 0.f, enc);
-      for (int c = 0; c < 72; c += 4) *reinterpret_cast<float4*>(eo + 72 + c) = make_float4(enc[c], enc[c + 1], enc[c + 2], enc[c + 3]);
+      if (miss) {
+        float sp[3], pu[3];
+        mc_sphere_point(q.pts + 3 * p, d, sp, pu);
+        ide_forward(c_ide_mc, sp, 0.f, tile[rank]);
+      }
+      warp_rows_store4<kMcTileLd, 18>(tile, eo + 72, q.ldeo, n_miss, lane);
     }
     if (q.human) {
-      const HumanGeo h = human_geo_fwd(q.pts + 3 * p, d, q.poses + 12 * p, 0.f);
-      const float var[2] = {0.f, 0.f};
-      float ipe[24];
-      ipe_forward(h.mean, var, ipe);
-      float* eh = q.EH + r * q.ldeh;
-      for (int c = 0; c < 24; c += 4) *reinterpret_cast<float4*>(eh + c) = make_float4(ipe[c], ipe[c + 1], ipe[c + 2], ipe[c + 3]);
-      q.hhit[r] = h.hit;
+      if (miss) {
+        const HumanGeo h = human_geo_fwd(q.pts + 3 * p, d, q.poses + 12 * p, 0.f);
+        const float var[2] = {0.f, 0.f};
+        ipe_forward(h.mean, var, tile[rank]);
+        q.hhit[row_o0 + rank] = h.hit;
+      }
+      warp_rows_store4<kMcTileLd, 6>(tile, q.EH + row_o0 * q.ldeh, q.ldeh, n_miss, lane);
     }
-  } else {
-    const long r = before;
-    q.slot[i] = ~int(r);
-    const float4 pd = reinterpret_cast<const float4*>(q.pos_depth)[i];
-    const float x[3] = {pd.x, pd.y, pd.z};
-    float pe[51];
-    pe_encode<3>(x, 8, pe);
-    float* ei = q.EI + r * q.ldei;
-    for (int c = 0; c < 51; ++c) ei[c] = pe[c];
-    ei[51] = 0.f;
-    float n[3], v[3], nv[3] = {-d[0], -d[1], -d[2]};
-    const float nr[3] = {nh.x, nh.y, nh.z};
-    normalize3(nr, n);
-    normalize3(nv, v);
-    const float vn = v[0] * n[0] + v[1] * n[1] + v[2] * n[2];
-    const float rf[3] = {vn * n[0] * 2.f - v[0], vn * n[1] * 2.f - v[1], vn * n[2] * 2.f - v[2]};
-    ide_forward(c_ide_mc, rf, 0.f, enc);
-    for (int c = 0; c < 72; c += 4) *reinterpret_cast<float4*>(ei + 52 + c) = make_float4(enc[c], enc[c + 1], enc[c + 2], enc[c + 3]);
+  }
+  // ---- hits -> inner rows
+  if (n_hit) {
+    float* ei = q.EI + row_i0 * q.ldei;
+    if (hit) {
+      q.slot[i] = ~int(row_i0 + rank);
+      const float4 pd = reinterpret_cast<const float4*>(q.pos_depth)[i];
+      const float x[3] = {pd.x, pd.y, pd.z};
+      pe_encode<3>(x, 8, tile[rank]);
+      tile[rank][51] = 0.f;
+    }
+    warp_rows_store4<kMcTileLd, 13>(tile, ei, q.ldei, n_hit, lane);
+    if (hit) {
+      float n[3], v[3], nv[3] = {-d[0], -d[1], -d[2]};
+      const float nr[3] = {nh.x, nh.y, nh.z};
+      normalize3(nr, n);
+      normalize3(nv, v);
+      const float vn = v[0] * n[0] + v[1] * n[1] + v[2] * n[2];
+      const float rf[3] = {vn * n[0] * 2.f - v[0], vn * n[1] * 2.f - v[1], vn * n[2] * 2.f - v[2]};
+      ide_forward(c_ide_mc, rf, 0.f, tile[rank]);
+    }
+    warp_rows_store4<kMcTileLd, 18>(tile, ei + 52, q.ldei, n_hit, lane);
   }
 }
 
@@ -372,7 +394,9 @@ int mc_classify(const McParams& q, cudaStream_t st) {
 int mc_fill(const McParams& q, cudaStream_t st) {
   const long N = long(q.P) * (q.Sd + q.Ss);
   if (N <= 0) return NERO_OK;
-  mc_fill_kernel<<<blocks_for_l(N, kClsBlock), kClsBlock, 0, st>>>(q, N);
+  static const cudaError_t attr = cudaFuncSetAttribute(mc_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMcFillSmem);
+  if (attr != cudaSuccess) return NERO_ERR_CUDA;
+  mc_fill_kernel<<<blocks_for_l(N, kClsBlock), kClsBlock, kMcFillSmem, st>>>(q, N);
   NERO_LAUNCH_CHECK();
   return NERO_OK;
 }

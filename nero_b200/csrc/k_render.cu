@@ -265,25 +265,21 @@ __global__ void row_axpy_kernel(const float* __restrict__ a, int lda, const floa
   }
 }
 
-// g = J_PE^T (U0 + USKIP)
-constexpr int kPeLd = 41;            // PE6 of 3 coordinates = 39 columns
-__global__ void __launch_bounds__(128) pe_grad_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ U0, int ldu,
-                                                      const float* __restrict__ US, int lds, float* G, const int* m_ptr, int m_cap) {
-  __shared__ float s_u[4][32][kPeLd], s_x[4][32][kPeLd];
+// g = J_PE^T (U0 + USKIP)     (row READS stay per thread: a thread walks its own row, every sector it touches is fetched
+// once and then served from L1 -- staging them through shared memory was measured 2x slower; only row WRITES are staged)
+__global__ void pe_grad_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ U0, int ldu,
+                               const float* __restrict__ US, int lds, float* G, const int* m_ptr, int m_cap) {
   const int M = load_count(m_ptr, m_cap);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int base = blockIdx.x * blockDim.x + warp * 32;
-  if (base >= M) return;
-  const int rows = min(32, M - base);
-  warp_rows_load<kPeLd>(s_u[warp], U0 + size_t(base) * ldu, ldu, US + size_t(base) * lds, lds, 39, rows, lane);
-  warp_rows_load<kPeLd>(s_x[warp], X0 + size_t(base) * ldx, ldx, nullptr, 0, 39, rows, lane);
-  if (lane >= rows) return;
-  float g[3];
-  pe_backward<3>(s_x[warp][lane], 6, s_u[warp][lane], g);
-  *reinterpret_cast<float4*>(G + size_t(base + lane) * 4) = make_float4(g[0], g[1], g[2], 0.f);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float u[39], g[3];
+  for (int c = 0; c < 39; ++c) u[c] = U0[size_t(i) * ldu + c] + US[size_t(i) * lds + c];
+  pe_backward<3>(X0 + size_t(i) * ldx, 6, u, g);
+  *reinterpret_cast<float4*>(G + size_t(i) * 4) = make_float4(g[0], g[1], g[2], 0.f);
 }
 
 // ubar_0 = J_PE dg  -> UB0[:, 0:39];  UB4[:, 217:256] = ubar_0 / sqrt2
+constexpr int kPeLd = 41;            // PE6 of 3 coordinates = 39 columns
 __global__ void __launch_bounds__(128) pe_tangent_kernel(const float* __restrict__ X0, int ldx, const float* __restrict__ DG, float* UB0,
                                                          int ld0, float* UB4, int ld4, const int* m_ptr, int m_cap) {
   __shared__ float s_x[4][32][kPeLd];
@@ -292,13 +288,10 @@ __global__ void __launch_bounds__(128) pe_tangent_kernel(const float* __restrict
   const int base = blockIdx.x * blockDim.x + warp * 32;
   if (base >= M) return;
   const int rows = min(32, M - base);
-  warp_rows_load<kPeLd>(s_x[warp], X0 + size_t(base) * ldx, ldx, nullptr, 0, 39, rows, lane);
   if (lane < rows) {
     const float4 dg4 = *reinterpret_cast<const float4*>(DG + size_t(base + lane) * 4);
     const float dg[3] = {dg4.x, dg4.y, dg4.z};
-    float t[39];
-    pe_tangent<3>(s_x[warp][lane], 6, dg, t);
-    for (int c = 0; c < 39; ++c) s_x[warp][lane][c] = t[c];
+    pe_tangent<3>(X0 + size_t(base + lane) * ldx, 6, dg, s_x[warp][lane]);
   }
   warp_rows_store<kPeLd>(s_x[warp], UB0 + size_t(base) * ld0, ld0, 39, rows, lane);
   warp_rows_store<kPeLd>(s_x[warp], UB4 + size_t(base) * ld4 + 217, ld4, 39, rows, lane, kInvSqrt2);

@@ -55,7 +55,6 @@ struct ShadePrepParams {
 constexpr int kPrepTileLd = 73;     // 72 columns + 1
 struct PrepTile { float t[4][32][kPrepTileLd]; };
 #define tile_store_rows warp_rows_store<kPrepTileLd>
-#define tile_load_rows warp_rows_load<kPrepTileLd>
 
 __global__ void __launch_bounds__(128) shade_prep_fwd_kernel(const ShadePrepParams q) {
   __shared__ PrepTile sm;
@@ -84,24 +83,24 @@ __global__ void __launch_bounds__(128) shade_prep_fwd_kernel(const ShadePrepPara
   pe_encode<3>(x, q.pos_freq, mine);
   tile_store_rows(tile, e + E_PE8X, q.lde, 3 + 6 * q.pos_freq, rows, lane);
   ide_forward(c_ide, rf, rough, mine);
-  tile_store_rows(tile, e + E_IDER, q.lde, 72, rows, lane);
+  warp_rows_store4<kPrepTileLd, 18>(tile, e + E_IDER, q.lde, rows, lane);
   ide_forward(c_ide, n, 1.0f, mine);
-  tile_store_rows(tile, e + (q.sphere ? ES_IDEN : E_IDEN), q.lde, 72, rows, lane);
+  warp_rows_store4<kPrepTileLd, 18>(tile, e + (q.sphere ? ES_IDEN : E_IDEN), q.lde, rows, lane);
   if (q.sphere) {
     float sd[3];
     sphere_dir_fwd(x, rf, sd);
     ide_forward(c_ide, sd, rough, mine);
-    tile_store_rows(tile, e + ES_IDESR, q.lde, 72, rows, lane);
+    warp_rows_store4<kPrepTileLd, 18>(tile, e + ES_IDESR, q.lde, rows, lane);
     sphere_dir_fwd(x, n, sd);
     ide_forward(c_ide, sd, 1.0f, mine);
-    tile_store_rows(tile, e + ES_IDESN, q.lde, 72, rows, lane);
+    warp_rows_store4<kPrepTileLd, 18>(tile, e + ES_IDESN, q.lde, rows, lane);
   }
   float hit = 0.f;
   if (q.human_poses) {
     const HumanGeo h = human_geo_fwd(x, rf, q.human_poses + size_t(r) * 12, rough);
     const float var2[2] = {h.var, h.var};
     ipe_forward(h.mean, var2, mine);
-    tile_store_rows(tile, q.EH + size_t(base) * q.ldeh, q.ldeh, 24, rows, lane);
+    warp_rows_store4<kPrepTileLd, 6>(tile, q.EH + size_t(base) * q.ldeh, q.ldeh, rows, lane);
     hit = h.hit;
   }
   if (ok) {
@@ -124,17 +123,11 @@ struct ShadePrepBwdParams {
   int sphere;
 };
 
-__global__ void __launch_bounds__(128) shade_prep_bwd_kernel(const ShadePrepBwdParams q) {
-  __shared__ PrepTile sm;
+// (row reads stay per thread -- see pe_grad_kernel; this kernel only writes 5 floats per sample)
+__global__ void shade_prep_bwd_kernel(const ShadePrepBwdParams q) {
   const int M = load_count2(q.m_ptr, q.m_cap);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int base = blockIdx.x * blockDim.x + warp * 32;
-  if (base >= M) return;                       // whole warp
-  const int rows = min(32, M - base);
-  const int i = min(base + lane, M - 1);
-  const bool ok = base + lane < M;
-  float (*tile)[kPrepTileLd] = sm.t[warp];
-  const float* mine = tile[lane];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
   const int r = q.ray_in[i];
   const float4 g4 = *reinterpret_cast<const float4*>(q.G + size_t(i) * 4);
   const float4 p4 = *reinterpret_cast<const float4*>(q.pts + size_t(i) * 4);
@@ -145,37 +138,35 @@ __global__ void __launch_bounds__(128) shade_prep_bwd_kernel(const ShadePrepBwdP
   float n[3], v[3], rf[3], NoV;
   shade_geometry_fwd(g, view, n, v, rf, &NoV);
   const float rough = q.OUTS[size_t(i) * O_LDIM + O_ROUGH];
-  const float* dir0 = q.dE_dir + size_t(base) * q.ld_dir;
-  const float* dif0 = q.dE_dif + size_t(base) * q.ld_dif;
-  tile_load_rows(tile, dir0, q.ld_dir, q.dE_inn + size_t(base) * q.ld_inn, q.ld_inn, 72, rows, lane);
+  float dide[72];
+  for (int c = 0; c < 72; ++c) dide[c] = q.dE_dir[size_t(i) * q.ld_dir + c] + q.dE_inn[size_t(i) * q.ld_inn + c];
   float dr[3] = {0.f, 0.f, 0.f}, dnrm[3] = {0.f, 0.f, 0.f};
-  float drough = ide_backward(c_ide, rf, rough, mine, dr);
-  tile_load_rows(tile, dif0, q.ld_dif, nullptr, 0, 72, rows, lane);
-  ide_backward(c_ide, n, 1.0f, mine, dnrm);
+  float drough = ide_backward(c_ide, rf, rough, dide, dr);
+  for (int c = 0; c < 72; ++c) dide[c] = q.dE_dif[size_t(i) * q.ld_dif + c];
+  ide_backward(c_ide, n, 1.0f, dide, dnrm);
   if (q.sphere) {      // the second halves of the two outer_light inputs: encodings of the sphere exit directions
     float sd[3], dsd[3] = {0.f, 0.f, 0.f};
     sphere_dir_fwd(x, rf, sd);
-    tile_load_rows(tile, dir0 + 72, q.ld_dir, nullptr, 0, 72, rows, lane);
-    drough += ide_backward(c_ide, sd, rough, mine, dsd);
+    for (int c = 0; c < 72; ++c) dide[c] = q.dE_dir[size_t(i) * q.ld_dir + 72 + c];
+    drough += ide_backward(c_ide, sd, rough, dide, dsd);
     sphere_dir_bwd(x, rf, dsd, dr);
     sphere_dir_fwd(x, n, sd);
     dsd[0] = dsd[1] = dsd[2] = 0.f;
-    tile_load_rows(tile, dif0 + 72, q.ld_dif, nullptr, 0, 72, rows, lane);
-    ide_backward(c_ide, sd, 1.0f, mine, dsd);
+    for (int c = 0; c < 72; ++c) dide[c] = q.dE_dif[size_t(i) * q.ld_dif + 72 + c];
+    ide_backward(c_ide, sd, 1.0f, dide, dsd);
     sphere_dir_bwd(x, n, dsd, dnrm);
   }
   if (q.human_poses) {
     const float* pose = q.human_poses + size_t(r) * 12;
     const HumanGeo h = human_geo_fwd(x, rf, pose, rough);
-    tile_load_rows(tile, q.dEH + size_t(base) * q.ld_eh, q.ld_eh, nullptr, 0, 24, rows, lane);
     if (h.hit > 0.f) {
-      float dmean[2], dvar[2];
+      float deh[24], dmean[2], dvar[2];
+      for (int c = 0; c < 24; ++c) deh[c] = q.dEH[size_t(i) * q.ld_eh + c];
       const float var2[2] = {h.var, h.var};
-      ipe_backward(h.mean, var2, mine, dmean, dvar);
+      ipe_backward(h.mean, var2, deh, dmean, dvar);
       drough += human_geo_bwd(x, rf, pose, rough, dmean, dvar[0] + dvar[1], dr);
     }
   }
-  if (!ok) return;
   q.DOUTS[size_t(i) * O_LDIM + O_ROUGH] += drough * rough * (1.0f - rough);
   float dg[3] = {0.f, 0.f, 0.f};
   shade_geometry_bwd(g, n, v, NoV, dnrm, dr, q.dNoV[i], dg);

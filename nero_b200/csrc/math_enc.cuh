@@ -15,9 +15,10 @@ NERO_HD void pe_encode(const float* x, int L, float* out, float scale = 1.0f) {
   float f = 1.0f;
   for (int k = 0; k < L; ++k) {
     for (int c = 0; c < D; ++c) {
-      const float a = x[c] * f;
-      out[D + (2 * k) * D + c] = sinf(a) * scale;
-      out[D + (2 * k + 1) * D + c] = cosf(a) * scale;
+      float sn, cs;
+      sincosf(x[c] * f, &sn, &cs);             // one shared range reduction (the encodings are ~half of a fill kernel's instructions)
+      out[D + (2 * k) * D + c] = sn * scale;
+      out[D + (2 * k + 1) * D + c] = cs * scale;
     }
     f *= 2.0f;
   }

@@ -17,6 +17,21 @@ __device__ __forceinline__ void warp_rows_store(const float (*tile)[LD], float* 
     for (int c = lane; c < ncols; c += 32) dst[size_t(r) * ld + c] = tile[r][c] * scale;
   __syncwarp();
 }
+// The same for a compile-time row width of 4*NC4 columns: the (row, float4) pairs are dealt to the lanes round-robin, one
+// 16-byte store each (4x fewer instructions than the scalar walk, no idle lanes in the last partial pass).  Falls back to the
+// scalar walk when the destination is not 16-byte aligned.
+template <int LD, int NC4>
+__device__ __forceinline__ void warp_rows_store4(const float (*tile)[LD], float* dst, size_t ld, int rows, int lane, float scale = 1.0f) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) || (ld & 3)) { warp_rows_store<LD>(tile, dst, ld, 4 * NC4, rows, lane, scale); return; }
+  __syncwarp();
+  const int total = rows * NC4;
+  for (int idx = lane; idx < total; idx += 32) {
+    const int r = idx / NC4, q = idx - r * NC4;
+    const float* t = tile[r] + 4 * q;
+    *reinterpret_cast<float4*>(dst + size_t(r) * ld + 4 * q) = make_float4(t[0] * scale, t[1] * scale, t[2] * scale, t[3] * scale);
+  }
+  __syncwarp();
+}
 // tile[r][c] = a[r][c] (+ b[r][c])
 template <int LD>
 __device__ __forceinline__ void warp_rows_load(float (*tile)[LD], const float* a, size_t lda, const float* b, size_t ldb, int ncols,
