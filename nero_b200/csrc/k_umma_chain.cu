@@ -30,6 +30,7 @@
 #include <unordered_map>
 
 #include "umma_common.cuh"
+#include "tma.cuh"
 
 namespace nero {
 
@@ -131,23 +132,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-
-// TMA: 2-D tiled load global -> shared (arrives on an mbarrier with the box byte count), store shared -> global
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int r0, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(r0)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int r0) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(r0)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // write 16 fp32 values of this lane's row (columns c0..c0+15 of the next A operand) as packed split-bf16 into TMEM
 __device__ __forceinline__ void write_a16(uint32_t tmem_lane_base, int c0, const float* y) {
@@ -709,59 +693,10 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-struct MapKey {
-  uintptr_t ptr; int ld, rows, cols;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && ld == o.ld && rows == o.rows && cols == o.cols; }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    return std::hash<uintptr_t>()(k.ptr) ^ (std::hash<long long>()((long long)k.ld << 40 ^ (long long)k.rows << 12 ^ k.cols) * 0x9E3779B97F4A7C15ull);
-  }
-};
-
 // a [rows x cols] fp32 window (leading dimension ld) as a 2-D tensor map with [128 x 16] SWIZZLE_64B boxes
-static bool tma_eligible(const float* ptr, int ld, int cols) {
-  return ptr && cols >= 8 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0;
-}
+static bool tma_eligible(const float* ptr, int ld, int cols) { return tma_eligible_f32(ptr, ld, cols); }
 static int make_map(CUtensorMap* out, const float* ptr, int ld, int rows, int cols) {
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  static std::mutex mu;
-  const MapKey key{reinterpret_cast<uintptr_t>(ptr), ld, rows, cols};
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it != cache.end()) { *out = it->second; return NERO_OK; }
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return NERO_ERR_CUDA;
-  const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
-  const cuuint32_t box[2] = {16, CH_BM};
-  const cuuint32_t estr[2] = {1, 1};
-  CUtensorMap m;
-  const CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) {
-    fprintf(stderr, "nero_b200: cuTensorMapEncodeTiled failed (%d) for ptr %p ld %d rows %d cols %d\n", int(rc), (const void*)ptr, ld, rows, cols);
-    return NERO_ERR_CUDA;
-  }
-  if (cache.size() > 4096) cache.clear();
-  cache.emplace(key, m);
-  *out = m;
-  return NERO_OK;
+  return tma_make_map_f32(out, ptr, ld, rows, cols, 16, CH_BM, 64);
 }
 
 int chain_dispatch(const ChainParams& p, cudaStream_t stream) {

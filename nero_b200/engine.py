@@ -725,10 +725,12 @@ class ShapeEngine:
             return 0
         sel = w['SEL']
         if cnt > maxp:   # renderer.py:535-541 random subset
-            idx = perm if perm is not None else torch.randperm(cnt, device=self.dev)
-            # the compaction kernel orders candidates only within a block; the reference indexes them in sample order
-            # (boolean-mask gather), so restore that order before the permutation picks its subset
-            sel = torch.sort(sel[:cnt])[0][idx[:maxp].to(self.dev)].contiguous()
+            if perm is not None:
+                # a caller-supplied permutation (parity tests) refers to the reference's candidate order: the compaction kernel
+                # orders candidates only within a block, the reference indexes them in sample order (boolean-mask gather)
+                sel = torch.sort(sel[:cnt])[0][perm[:maxp].to(self.dev)].contiguous()
+            else:       # a uniformly random subset does not depend on the order the candidates are listed in
+                sel = sel[:cnt][torch.randperm(cnt, device=self.dev)[:maxp]].contiguous()
             cnt = maxp
             w['SEL_SUB'] = sel
         return self._occ_march(sel, None, cnt)
