@@ -725,12 +725,11 @@ class ShapeEngine:
             return 0
         sel = w['SEL']
         if cnt > maxp:   # renderer.py:535-541 random subset
-            if perm is not None:
-                # a caller-supplied permutation (parity tests) refers to the reference's candidate order: the compaction kernel
-                # orders candidates only within a block, the reference indexes them in sample order (boolean-mask gather)
-                sel = torch.sort(sel[:cnt])[0][perm[:maxp].to(self.dev)].contiguous()
-            else:       # a uniformly random subset does not depend on the order the candidates are listed in
-                sel = sel[:cnt][torch.randperm(cnt, device=self.dev)[:maxp]].contiguous()
+            idx = perm if perm is not None else torch.randperm(cnt, device=self.dev)
+            # the compaction kernel orders candidates only within a block (and the blocks by atomic arrival); the reference
+            # indexes them in sample order (boolean-mask gather): restore that order before the permutation picks its subset,
+            # which also makes the subset a function of the RNG state alone (run-to-run determinism under a fixed seed)
+            sel = torch.sort(sel[:cnt])[0][idx[:maxp].to(self.dev)].contiguous()
             cnt = maxp
             w['SEL_SUB'] = sel
         return self._occ_march(sel, None, cnt)

@@ -132,6 +132,31 @@ def test_wgrad(M, N, K, two):
     assert e_v < 3e-5 and e_g < 3e-5 and e_b < 1e-5
 
 
+def test_wgrad_device_row_count_masks_stale_rows():
+    """Rows >= the device-side count hold stale data (here NaN / inf): the TMA-fed producers must zero them while converting."""
+    from nero_b200 import ops
+    dev = torch.device('cuda')
+    M, cap, N, K = 12345, 20000, 256, 256
+    L, W, b = _mk_layer(ops, N, K, dev)
+    ws = ops.WgradWorkspace(dev)
+    dY = torch.randn(cap, 256, device=dev) * 0.1
+    X = torch.randn(cap, 256, device=dev)
+    dY[M:] = float('nan')
+    X[M:] = float('inf')
+    m_ptr = torch.tensor([M], dtype=torch.int32, device=dev)
+    gw, gg, gb = torch.zeros_like(L.weight), torch.zeros_like(L.g), torch.zeros(N, device=dev)
+    ops.wgrad(ws, ops.Mat(dY), N, ops.Mat(X), L.k_valid, L, gw, gg, gb, m_ptr=m_ptr, m_cap=cap)
+    torch.cuda.synchronize()
+    v = L.weight.double().requires_grad_(True)
+    g = L.g.double().requires_grad_(True)
+    dW = dY[:M].double().t() @ X[:M].double()
+    ((g * v / v.norm(dim=1, keepdim=True)) * dW).sum().backward()
+    sc = float(dW.abs().max())
+    assert torch.isfinite(gw).all() and torch.isfinite(gb).all()
+    assert float((gw.double() - v.grad).abs().max()) / sc < 3e-5
+    assert float((gb.double() - dY[:M].double().sum(0)).abs().max()) / float(dY[:M].abs().sum(0).max()) < 1e-5
+
+
 @pytest.mark.parametrize('M', [3000, 45001])
 def test_chain_matches_layerwise_and_fp64(M):
     """Fused chain (A operand in TMEM) vs fp64 torch: 3 softplus layers with the skip-concat, then a linear head;
