@@ -12,12 +12,9 @@
 // The optional second pair implements the double-backward term of the SDF network,
 //   dW_k = abar_k^T h_k + v_k^T ubar_k      (SURVEY.md Appendix A.3, K4),
 // in ONE accumulator.  Column sums of dY (bias gradient) are produced by the dY producer threads for free.
-#include <cstdlib>
-#include <mutex>
 
 #include "common.cuh"
 #include "ptx.cuh"
-#include "tma.cuh"
 
 namespace nero {
 
@@ -395,213 +392,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
   if (warp == kWgProdWarps) tmem_dealloc<256>(tmem_base);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// TMA-fed variant of the MN-major kernel (the one the training step uses).  In the kernel above the 16 producer warps
-// alternate between "issue global loads" and "convert + store": every warp is in the same phase (the stage barriers
-// synchronise them), so HBM idles while they convert -- 3.6 TB/s of the 6.6 TB/s peak.  Here a dedicated thread streams the
-// raw fp32 row blocks ([32 samples x 128] of dY, [32 x NW] of X) into a shared-memory ring with TMA, always two or more
-// stages ahead, and the 16 warps only convert shared -> shared (raw fp32 -> split-bf16 MN-major planes).  Columns beyond
-// n_valid / k_valid are zero-filled by TMA (tensor-map extent); rows >= M (device-side count) are masked while converting.
-constexpr int WGT_BK = 32;                                   // samples per stage
-constexpr uint32_t kMnLboT = (WGT_BK / 8) * 1024;
-constexpr int kWgtThreads = (kWgProdWarps + 2) * 32;         // + MMA warp + TMA warp
-template <int NW> struct WgtCfg {
-  static constexpr uint32_t a_raw = WGT_BK * WG_BM * 4, b_raw = WGT_BK * NW * 4;      // fp32 row blocks
-  static constexpr uint32_t raw_stage = a_raw + b_raw;
-  static constexpr uint32_t a_plane = WG_BM * WGT_BK * 2, b_plane = NW * WGT_BK * 2;   // bf16 planes
-  static constexpr uint32_t bf_stage = 2 * a_plane + 2 * b_plane;                      // == raw_stage
-  static constexpr int bf_stages = 2;
-  static constexpr int raw_stages = ((220u * 1024u - bf_stages * bf_stage) / raw_stage) > 4 ? 4 : int((220u * 1024u - bf_stages * bf_stage) / raw_stage);
-  static constexpr uint32_t smem_bytes = bf_stages * bf_stage + raw_stages * raw_stage + 1024 + 256 + 512;
-  static_assert(raw_stages >= 2, "raw ring");
-};
-struct WgradTmaParams {
-  WgradParams p;
-  CUtensorMap maps[4];      // dY, X, dY2, X2
-};
-
-__device__ __forceinline__ uint32_t mn_chunk_offset_t(uint32_t chunk, uint32_t s) {   // chunk = feature/8, s = sample in stage
-  const uint32_t r = s & 7u;
-  return (chunk >> 3) * kMnLboT + (s >> 3) * kMnSbo + r * 128u + (((chunk & 7u) ^ r) << 4);
-}
-
-template <int NW>
-__global__ void __launch_bounds__(kWgtThreads, 1) umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams q) {
-  using Cfg = WgtCfg<NW>;
-  constexpr int SB = Cfg::bf_stages, SR = Cfg::raw_stages;
-  constexpr int CB = NW / 8;                 // 8-feature chunks per X row: 32 / 16 / 8
-  constexpr int SPW = 32 / CB;               // X sample rows per warp instruction: 1 / 2 / 4
-  constexpr int BT = WGT_BK / SPW;           // X warp-tasks per stage: 32 / 16 / 8
-  const WgradParams& p = q.p;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_bf = smem;
-  uint8_t* s_rawbuf = smem + SB * Cfg::bf_stage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawbuf + SR * Cfg::raw_stage);
-  uint64_t* bf_full = bars;                  // [SB] planes written (16 warps)
-  uint64_t* bf_empty = bars + SB;            // [SB] MMAs done reading
-  uint64_t* raw_full = bars + 2 * SB;        // [SR] TMA landed
-  uint64_t* raw_empty = bars + 2 * SB + SR;  // [SR] 16 warps done reading
-  uint64_t* tfull = bars + 2 * SB + 2 * SR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
-  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int M = p.m_ptr ? *p.m_ptr : p.m_cap;
-  if (M > p.m_cap) M = p.m_cap;
-  const int P = gridDim.x;
-  const int n0 = p.n0 + int(blockIdx.y) * WG_BM;
-  const int total_chunks = (M + WGT_BK - 1) / WGT_BK;
-  const int cpp = (total_chunks + P - 1) / P;
-  const int c_begin = min(total_chunks, int(blockIdx.x) * cpp), c_end = min(total_chunks, c_begin + cpp);
-  const int npairs = p.dY2 ? 2 : 1;
-  const int nc1 = c_end - c_begin;
-  const int nchunks = nc1 * npairs;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SB; ++s) { mbar_init(&bf_full[s], kWgProdWarps); mbar_init(&bf_empty[s], 1); }
-    for (int s = 0; s < SR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kWgProdWarps); }
-    mbar_init(tfull, 1);
-    fence_mbar_init();
-  }
-  if (threadIdx.x < 128) s_bias[threadIdx.x] = 0.0f;
-  if (warp == kWgProdWarps) tmem_alloc<256>(tmem_slot);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < kWgProdWarps) {
-    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint32_t a_chunk = lane & 15, a_row = 2 * warp + (lane >> 4);       // dY: one 8-feature chunk of one sample per thread
-    const uint32_t b_chunk = lane % CB, b_sub = lane / CB;
-    for (int g = 0; g < nchunks; ++g) {
-      const int sb = g % SB, sr = g % SR;
-      const int pair = g / nc1;
-      const int s0 = (c_begin + g % nc1) * WGT_BK;
-      uint8_t* bf = s_bf + sb * Cfg::bf_stage;
-      const uint8_t* raw = s_rawbuf + sr * Cfg::raw_stage;
-      mbar_wait(&raw_full[sr], (g / SR) & 1);
-      mbar_wait(&bf_empty[sb], ((g / SB) & 1) ^ 1);
-      {   // ---- dY rows -> A planes
-        const float4* src = reinterpret_cast<const float4*>(raw + a_row * (WG_BM * 4) + a_chunk * 32);
-        float4 v0 = src[0], v1 = src[1];
-        if (s0 + int(a_row) >= M) { v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0; }
-        uint32_t hw[4], lw[4];
-        wg_split2(v0.x, v0.y, hw[0], lw[0]); wg_split2(v0.z, v0.w, hw[1], lw[1]);
-        wg_split2(v1.x, v1.y, hw[2], lw[2]); wg_split2(v1.z, v1.w, hw[3], lw[3]);
-        const uint32_t off = mn_chunk_offset_t(a_chunk, a_row);
-        *reinterpret_cast<uint4*>(bf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(bf + Cfg::a_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        if (pair == 0) {
-          bsum[0] += v0.x; bsum[1] += v0.y; bsum[2] += v0.z; bsum[3] += v0.w;
-          bsum[4] += v1.x; bsum[5] += v1.y; bsum[6] += v1.z; bsum[7] += v1.w;
-        }
-      }
-#pragma unroll
-      for (int t = warp; t < BT; t += kWgProdWarps) {   // ---- X rows -> B planes
-        const uint32_t row = uint32_t(t) * SPW + b_sub;
-        const float4* src = reinterpret_cast<const float4*>(raw + Cfg::a_raw + row * (NW * 4) + b_chunk * 32);
-        float4 v0 = src[0], v1 = src[1];
-        if (s0 + int(row) >= M) { v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0; }
-        uint32_t hw[4], lw[4];
-        wg_split2(v0.x, v0.y, hw[0], lw[0]); wg_split2(v0.z, v0.w, hw[1], lw[1]);
-        wg_split2(v1.x, v1.y, hw[2], lw[2]); wg_split2(v1.z, v1.w, hw[3], lw[3]);
-        const uint32_t off = mn_chunk_offset_t(b_chunk, row);
-        *reinterpret_cast<uint4*>(bf + 2 * Cfg::a_plane + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(bf + 2 * Cfg::a_plane + Cfg::b_plane + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(&bf_full[sb]); mbar_arrive(&raw_empty[sr]); }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], 16);
-      if (lane < 16) atomicAdd(&s_bias[a_chunk * 8 + j], bsum[j]);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
-    if (warp < 4) {
-      // -------- epilogue: TMEM tile -> added into the layer's accumulator
-      mbar_wait(tfull, 0);
-      tcgen05_fence_after();
-      wg_epilogue<NW>(p, tmem_base, warp, lane, n0, nchunks > 0, s_bias);
-    }
-  } else if (warp == kWgProdWarps) {
-    // -------- MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16_mn(WG_BM, NW);
-    for (int g = 0; g < nchunks; ++g) {
-      const int s = g % SB;
-      mbar_wait(&bf_full[s], (g / SB) & 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t a_hi = smem_u32(s_bf + s * Cfg::bf_stage);
-        const uint32_t a_lo = a_hi + Cfg::a_plane;
-        const uint32_t b_hi = a_hi + 2 * Cfg::a_plane;
-        const uint32_t b_lo = b_hi + Cfg::b_plane;
-#pragma unroll
-        for (int k = 0; k < WGT_BK / 16; ++k) {     // 16 samples = two 8-row groups per MMA
-          const uint32_t ko = k * 2 * kMnSbo;
-          const uint64_t dah = make_desc_mn_sw128(a_hi + ko, kMnLboT, kMnSbo), dal = make_desc_mn_sw128(a_lo + ko, kMnLboT, kMnSbo);
-          const uint64_t dbh = make_desc_mn_sw128(b_hi + ko, kMnLboT, kMnSbo), dbl = make_desc_mn_sw128(b_lo + ko, kMnLboT, kMnSbo);
-          umma_bf16(tmem_base, dal, dbh, idesc, (g | k) != 0);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1);
-          umma_bf16(tmem_base, dah, dbh, idesc, 1);
-        }
-        umma_commit(&bf_empty[s]);
-        if (g == nchunks - 1) umma_commit(tfull);
-      }
-      __syncwarp();
-    }
-    if (nchunks == 0 && elect_one()) mbar_arrive(tfull);
-    __syncwarp();
-  } else {
-    // -------- TMA producer: raw fp32 row blocks of dY (columns n0..n0+127) and X (columns k0..k0+NW-1)
-    if (lane == 0) {
-      for (int g = 0; g < nchunks; ++g) {
-        const int sr = g % SR;
-        const int pair = g / nc1;
-        const int s0 = (c_begin + g % nc1) * WGT_BK;
-        uint8_t* raw = s_rawbuf + sr * Cfg::raw_stage;
-        mbar_wait(&raw_empty[sr], ((g / SR) & 1) ^ 1);
-        mbar_arrive_expect_tx(&raw_full[sr], Cfg::raw_stage);
-        tma_load_2d(raw, &q.maps[2 * pair], n0, s0, &raw_full[sr]);
-        tma_load_2d(raw + Cfg::a_raw, &q.maps[2 * pair + 1], p.k0, s0, &raw_full[sr]);
-      }
-    }
-    __syncwarp();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == kWgProdWarps) tmem_dealloc<256>(tmem_base);
-}
-
-template <int NW>
-static int launch_wgrad_tma(const WgradParams& p, int P, int n_tiles, cudaStream_t stream) {
-  using Cfg = WgtCfg<NW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(umma_wgrad_tma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
-      return NERO_ERR_CUDA;
-    attr_set = true;
-  }
-  static WgradTmaParams q;        // host calls are serialised (Python GIL); the struct is copied at launch
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  q.p = p;
-  // tensor-map windows: the valid columns only (TMA zero-fills the rest of a box), all m_cap rows
-  if (tma_make_map_f32(&q.maps[0], p.dY, p.ldy, p.m_cap, p.n_valid, WG_BM, WGT_BK, 0) != NERO_OK) return NERO_ERR_CUDA;
-  if (tma_make_map_f32(&q.maps[1], p.X, p.ldx, p.m_cap, p.k_valid, NW, WGT_BK, 0) != NERO_OK) return NERO_ERR_CUDA;
-  if (p.dY2) {
-    if (tma_make_map_f32(&q.maps[2], p.dY2, p.ldy2, p.m_cap, p.n_valid, WG_BM, WGT_BK, 0) != NERO_OK) return NERO_ERR_CUDA;
-    if (tma_make_map_f32(&q.maps[3], p.X2, p.ldx2, p.m_cap, p.k_valid, NW, WGT_BK, 0) != NERO_OK) return NERO_ERR_CUDA;
-  }
-  umma_wgrad_tma_kernel<NW><<<dim3(P, n_tiles), kWgtThreads, Cfg::smem_bytes, stream>>>(q);
-  NERO_LAUNCH_CHECK();
-  return NERO_OK;
-}
-
-
 template <int NW>
 static int launch_wgrad_mn(const WgradParams& p, int P, int n_tiles, cudaStream_t stream) {
   using Cfg = WgCfg<NW>;
@@ -636,8 +426,11 @@ int wgrad_dispatch(WgradParams p, int n_rows_pad, int k_pad, int P, cudaStream_t
   if ((p.ld_partial & 3) || k_pad % 64 || n_rows_pad % 16 || P <= 0) return NERO_ERR_ARG;
   const int n_tiles = (n_rows_pad + 127) / 128;
   p.n0 = 0;
-  // the MN-major kernels copy rows in 16-byte pieces: they need 16-byte aligned rows and column origins; otherwise the
-  // transposing kernel runs
+  // the MN-major kernel copies rows in 16-byte pieces: it needs 16-byte aligned rows and column origins; otherwise the
+  // transposing kernel runs.
+  // (Tried in round 2 and removed: feeding the MN-major kernel from a TMA ring of raw fp32 row blocks [2 x 48 KB] with the 16
+  //  warps converting shared -> shared -- 81.6 us vs 71.3 us per 256x256 layer at 127 k rows, profiles/r02r_*: with only two
+  //  refillable stages the bytes in flight are no more than the register-staged loads already keep in flight.)
   auto al = [](const float* q, int ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld & 3) == 0); };
   const bool mn = al(p.dY, p.ldy) && al(p.X, p.ldx) && al(p.dY2, p.ldy2) && al(p.X2, p.ldx2);
   int k0 = 0;
@@ -645,11 +438,9 @@ int wgrad_dispatch(WgradParams p, int n_rows_pad, int k_pad, int P, cudaStream_t
     const int rem = k_pad - k0;
     p.k0 = k0;
     int rc;
-    // TMA box columns past the window are zero-filled, but the window itself must start inside the tensor
-    const bool tma = mn && k0 < p.k_valid && p.n_valid > 0;
-    if (rem >= 256) { rc = tma ? launch_wgrad_tma<256>(p, P, n_tiles, stream) : mn ? launch_wgrad_mn<256>(p, P, n_tiles, stream) : launch_wgrad<256>(p, P, n_tiles, stream); k0 += 256; }
-    else if (rem >= 128) { rc = tma ? launch_wgrad_tma<128>(p, P, n_tiles, stream) : mn ? launch_wgrad_mn<128>(p, P, n_tiles, stream) : launch_wgrad<128>(p, P, n_tiles, stream); k0 += 128; }
-    else { rc = tma ? launch_wgrad_tma<64>(p, P, n_tiles, stream) : mn ? launch_wgrad_mn<64>(p, P, n_tiles, stream) : launch_wgrad<64>(p, P, n_tiles, stream); k0 += 64; }
+    if (rem >= 256) { rc = mn ? launch_wgrad_mn<256>(p, P, n_tiles, stream) : launch_wgrad<256>(p, P, n_tiles, stream); k0 += 256; }
+    else if (rem >= 128) { rc = mn ? launch_wgrad_mn<128>(p, P, n_tiles, stream) : launch_wgrad<128>(p, P, n_tiles, stream); k0 += 128; }
+    else { rc = mn ? launch_wgrad_mn<64>(p, P, n_tiles, stream) : launch_wgrad<64>(p, P, n_tiles, stream); k0 += 64; }
     if (rc != NERO_OK) return rc;
   }
   return NERO_OK;

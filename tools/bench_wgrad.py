@@ -1,7 +1,7 @@
 """Developer micro-benchmark of the weight-gradient GEMM alone (run on the GPU box)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import torch
 from nero_b200 import ops
 from test_gemm_gpu import _mk_layer
