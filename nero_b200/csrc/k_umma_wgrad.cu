@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "umma_common.cuh"
 
 namespace nero {
 
@@ -236,25 +237,77 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const WgradPa
 // dimension (features) is the contiguous one: that is exactly an MN-major UMMA operand.  Producers therefore copy rows
 // as they lie -- two 16-byte global loads (8 features of one sample), split to bf16 hi/lo, one 16-byte shared store per
 // plane into the MN-major SWIZZLE_128B atom -- instead of transposing with scalar loads.
-// Stage layout per plane: [feature block of 64][sample group of 8][8 rows x 128 B]  (SBO = 1024, LBO = 8192).
+// Stage layout per plane: [feature block of 64][sample group of 8][8 rows x 128 B]  (SBO = 1024, LBO = 4096 with 32-sample stages).
 // Requires 16-byte aligned rows (ld % 4 == 0, column origin % 4 == 0); wgrad_dispatch checks and otherwise uses the
 // transposing kernel above.
-constexpr uint32_t kMnSbo = 1024, kMnLbo = (WG_BK / 8) * 1024;
+// The 16 producer warps work as TWO GROUPS on alternating 32-sample stages: while one group converts and stores its stage,
+// the other group's loads for the next stage are in flight.  (Measured neutral against all 16 warps sharing 64-sample stages,
+// 70.1 vs 70.7 us per 256x256 layer at 127 k rows: of those ~55 us are the main loop at 4.75 TB/s -- two-pair launches take
+// 125 us -- and ~15 us are fill, drain and the accumulate epilogue.)
+constexpr int MN_BK = 32, kMnGroupWarps = kWgProdWarps / 2;
+constexpr uint32_t kMnSbo = 1024, kMnLbo = (MN_BK / 8) * 1024;
+template <int NW> struct WgMnCfg {
+  static constexpr uint32_t a_plane = WG_BM * MN_BK * 2, b_plane = NW * MN_BK * 2;
+  static constexpr uint32_t stage_bytes = 2 * a_plane + 2 * b_plane;
+  static constexpr int stages = 4;
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + 1024 + 256 + 512;
+};
 
 __device__ __forceinline__ uint32_t mn_chunk_offset(uint32_t chunk, uint32_t s) {   // chunk = feature/8, s = sample in stage
   const uint32_t r = s & 7u;
   return (chunk >> 3) * kMnLbo + (s >> 3) * kMnSbo + r * 128u + (((chunk & 7u) ^ r) << 4);
 }
 
+// Epilogue of the MN-major kernel: all 16 producer warps move the 128 x NW accumulator tile TMEM -> shared (thread = row, as
+// TMEM hands it out) and then ADD it into the layer's accumulator row by row, 32 lanes x 16 bytes = 512 contiguous bytes per
+// reduction instruction (the thread-per-row epilogue of the transposing kernel issues every 16-byte reduction to a different
+// row: 32 separate L2 transactions per instruction).
+// CTAs start at different rows so that they do not all hit the same L2 lines at the same time.
+template <int NW>
+__device__ __forceinline__ void wg_epilogue_rows(const WgradParams& p, uint32_t tmem_base, float* tile, int warp, int lane, int n0,
+                                                 const float* s_bias) {
+  constexpr int LD = NW + 4;                              // row stride of the shared tile (floats): 16-byte aligned, 4 banks off
+  constexpr int SLICE = NW / 4;                           // columns per warp: 64 / 32 / 16
+  const int quarter = warp & 3, slice = warp >> 2;        // TMEM lane quarter this warp may read, column slice it takes
+  {
+    const int row = quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(slice * SLICE);
+    float* dst = tile + row * LD + slice * SLICE;
+#pragma unroll
+    for (int c = 0; c < SLICE; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
+  const int r_first = (int(blockIdx.x) * 5) & 127;
+  for (int i = warp; i < WG_BM; i += kWgProdWarps) {
+    const int r = (i + r_first) & 127;
+    const int orow = n0 + r;
+    if (orow >= p.rows_partial) continue;
+    float* prow = p.partial + size_t(orow) * p.ld_partial + p.k0;
+#pragma unroll
+    for (int c = lane * 4; c < NW; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(tile + r * LD + c);
+      red_add_v4(prow + c, v.x, v.y, v.z, v.w);
+    }
+    if (lane == 0 && p.bias_partial && p.k0 == 0) atomicAdd(&p.bias_partial[orow], s_bias[r]);
+  }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const WgradParams p) {
-  using Cfg = WgCfg<NW>;
+  using Cfg = WgMnCfg<NW>;
   constexpr int STAGES = Cfg::stages;
   constexpr int CB = NW / 8;                 // 16-byte chunks per X row
   constexpr int SPW = 32 / CB;               // X sample rows per warp instruction
-  constexpr int TASKS = 32 + WG_BK / SPW;    // per stage: 32 dY tasks (2 sample rows each) + X tasks
-  constexpr int TPW = TASKS / kWgProdWarps;  // tasks per warp: 6 / 4 / 3
-  static_assert(TASKS % kWgProdWarps == 0 && TPW >= 2, "task split");
+  constexpr int ATASKS = MN_BK / 2;          // dY tasks (2 sample rows each)
+  constexpr int TASKS = ATASKS + MN_BK / SPW;   // + X tasks: 48 / 32 / 24 per stage
+  constexpr int TPW = TASKS / kMnGroupWarps;    // tasks per warp of the stage's group: 6 / 4 / 3
+  static_assert(TASKS % kMnGroupWarps == 0 && TPW >= 2 && STAGES % 2 == 0, "task split");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes);
@@ -269,7 +322,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
   if (M > p.m_cap) M = p.m_cap;
   const int P = gridDim.x;
   const int n0 = p.n0 + int(blockIdx.y) * WG_BM;
-  const int total_chunks = (M + WG_BK - 1) / WG_BK;
+  const int total_chunks = (M + MN_BK - 1) / MN_BK;
   const int cpp = (total_chunks + P - 1) / P;
   const int c_begin = min(total_chunks, int(blockIdx.x) * cpp), c_end = min(total_chunks, c_begin + cpp);
   const int npairs = p.dY2 ? 2 : 1;
@@ -277,7 +330,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
   const int nchunks = nc1 * npairs;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kWgProdWarps); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kMnGroupWarps); mbar_init(&empty[s], 1); }
     mbar_init(tfull, 1);
     fence_mbar_init();
   }
@@ -294,11 +347,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
     const uint32_t a_chunk = lane & 15, a_sub = lane >> 4;
     const uint32_t b_chunk = lane % CB, b_sub = lane / CB;
     const int a_col = n0 + int(a_chunk) * 8, b_col = p.k0 + int(b_chunk) * 8;
-    for (int g = 0; g < nchunks; ++g) {
+    const int group = warp / kMnGroupWarps, wi = warp % kMnGroupWarps;
+    for (int g = group; g < nchunks; g += 2) {        // this group's stages
       const int s = g % STAGES;
       const int pair = g / nc1;
       const int chunk = c_begin + g % nc1;
-      const int s0 = chunk * WG_BK;
+      const int s0 = chunk * MN_BK;
       uint8_t* st = smem + s * Cfg::stage_bytes;
       const float* srcA = pair ? p.dY2 : p.dY;
       const int ldA = pair ? p.ldy2 : p.ldy;
@@ -307,9 +361,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
       float4 v[TPW][2];
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
-        const int t = warp + kWgProdWarps * i;
-        const bool isA = t < 32;                                 // warp-uniform
-        const int sl = isA ? 2 * t + int(a_sub) : (t - 32) * SPW + int(b_sub);
+        const int t = wi + kMnGroupWarps * i;
+        const bool isA = t < ATASKS;                             // warp-uniform
+        const int sl = isA ? 2 * t + int(a_sub) : (t - ATASKS) * SPW + int(b_sub);
         const int srow = s0 + sl;
         const int col = isA ? a_col : b_col;
         const int lim = isA ? p.n_valid : p.k_valid;
@@ -321,9 +375,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
       mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
-        const int t = warp + kWgProdWarps * i;
-        const bool isA = t < 32;
-        const int sl = isA ? 2 * t + int(a_sub) : (t - 32) * SPW + int(b_sub);
+        const int t = wi + kMnGroupWarps * i;
+        const bool isA = t < ATASKS;
+        const int sl = isA ? 2 * t + int(a_sub) : (t - ATASKS) * SPW + int(b_sub);
         const int col = isA ? a_col : b_col;
         const int lim = isA ? p.n_valid : p.k_valid;
         float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
@@ -332,8 +386,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) wg_split2(x[2 * j], x[2 * j + 1], hw[j], lw[j]);
-        uint8_t* hi = isA ? st : st + 2 * kWgABytes;
-        uint8_t* lo = isA ? st + kWgABytes : st + 2 * kWgABytes + Cfg::b_plane;
+        uint8_t* hi = isA ? st : st + 2 * Cfg::a_plane;
+        uint8_t* lo = isA ? st + Cfg::a_plane : st + 2 * Cfg::a_plane + Cfg::b_plane;
         const uint32_t off = mn_chunk_offset(isA ? a_chunk : b_chunk, uint32_t(sl));
         *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -352,12 +406,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
       if (lane < 16) atomicAdd(&s_bias[a_chunk * 8 + j], bsum[j]);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kWgProdWarps * 32));
-    if (warp < 4) {
-      // -------- epilogue: TMEM tile -> added into the layer's accumulator
-      mbar_wait(tfull, 0);
-      tcgen05_fence_after();
-      wg_epilogue<NW>(p, tmem_base, warp, lane, n0, nchunks > 0, s_bias);
-    }
+    // -------- epilogue: TMEM tile -> shared (the stage buffers are free once the last MMA has completed) -> accumulator rows
+    mbar_wait(tfull, 0);
+    tcgen05_fence_after();
+    if (nchunks > 0) wg_epilogue_rows<NW>(p, tmem_base, reinterpret_cast<float*>(smem), warp, lane, n0, s_bias);
   } else {
     // -------- MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16_mn(WG_BM, NW);
@@ -367,11 +419,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * Cfg::stage_bytes);
-        const uint32_t a_lo = a_hi + kWgABytes;
-        const uint32_t b_hi = a_hi + 2 * kWgABytes;
+        const uint32_t a_lo = a_hi + Cfg::a_plane;
+        const uint32_t b_hi = a_hi + 2 * Cfg::a_plane;
         const uint32_t b_lo = b_hi + Cfg::b_plane;
 #pragma unroll
-        for (int k = 0; k < WG_BK / 16; ++k) {     // 16 samples = two 8-row groups per MMA
+        for (int k = 0; k < MN_BK / 16; ++k) {     // 16 samples = two 8-row groups per MMA
           const uint32_t ko = k * 2 * kMnSbo;
           const uint64_t dah = make_desc_mn_sw128(a_hi + ko, kMnLbo, kMnSbo), dal = make_desc_mn_sw128(a_lo + ko, kMnLbo, kMnSbo);
           const uint64_t dbh = make_desc_mn_sw128(b_hi + ko, kMnLbo, kMnSbo), dbl = make_desc_mn_sw128(b_lo + ko, kMnLbo, kMnSbo);
@@ -394,7 +446,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_mn_kernel(const Wgra
 
 template <int NW>
 static int launch_wgrad_mn(const WgradParams& p, int P, int n_tiles, cudaStream_t stream) {
-  using Cfg = WgCfg<NW>;
+  using Cfg = WgMnCfg<NW>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(umma_wgrad_mn_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes) != cudaSuccess)
@@ -430,7 +482,10 @@ int wgrad_dispatch(WgradParams p, int n_rows_pad, int k_pad, int P, cudaStream_t
   // transposing kernel runs.
   // (Tried in round 2 and removed: feeding the MN-major kernel from a TMA ring of raw fp32 row blocks [2 x 48 KB] with the 16
   //  warps converting shared -> shared -- 81.6 us vs 71.3 us per 256x256 layer at 127 k rows, profiles/r02r_*: with only two
-  //  refillable stages the bytes in flight are no more than the register-staged loads already keep in flight.)
+  //  refillable stages the bytes in flight are no more than the register-staged loads already keep in flight;
+  //  and computing both 128-row tiles of a 256-row layer in one CTA [32-sample stages, X converted once]: 85.0 us,
+  //  profiles/r02t_*.  The loop is bound by load latency + conversion time per stage, i.e. by the bytes one stage keeps in
+  //  flight, not by the amount of conversion work.)
   auto al = [](const float* q, int ld) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld & 3) == 0); };
   const bool mn = al(p.dY, p.ldy) && al(p.X, p.ldx) && al(p.dY2, p.ldy2) && al(p.X2, p.ldx2);
   int k0 = 0;
