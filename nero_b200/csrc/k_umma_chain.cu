@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
     t.rowoff = uint32_t(rl) * 64u;
     t.sw = uint32_t((rl >> 1) & 3) << 4;
     const uint32_t tl = tmem_base + (uint32_t(t.q * 32) << 16);
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, layer_seq = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += tile_step) {
       const int rows_valid = min(CH_BM, M - tile * CH_BM);
       const long row = long(tile) * CH_BM + rl;
@@ -480,9 +480,14 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
       if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(a_ready + 1); }
       for (int l = 0; l < p.n_layers; ++l) {
         const ChainLayerDev& L = p.L[l];
-        // bias of this layer -> smem buffer (l & 1): written while the MMAs run; the named barrier below orders it
-        // against the reads (two buffers + one barrier per layer make the reuse race-free)
-        float* sb = s_bias2 + (l & 1) * 256;
+        // bias of this layer -> one of two smem buffers: written while the MMAs run; the named barrier below orders it
+        // against the reads (two buffers + one barrier per layer make the reuse race-free).  The buffers alternate with a
+        // counter that runs ACROSS tiles: indexed by (l & 1), a chain with an odd number of layers used the same buffer for
+        // the last layer of one tile and the first layer of the next, and a warp that was a whole A0 conversion ahead
+        // overwrote the bias the slower warps were still adding (seen as rare wrong SDF values of the 9-layer sampling
+        // chain when the weight images were cold in L2; tools/stress_chain.py)
+        float* sb = s_bias2 + (layer_seq & 1u) * 256;
+        ++layer_seq;
         {
           const int i = warp * 32 + lane;
           if (i < 256) sb[i] = (L.bias && i < L.n_bias) ? __ldg(L.bias + i) : 0.0f;
