@@ -38,7 +38,9 @@ def _worker(rank, world, port, q):
     torch.set_num_threads(2)
     sd = build_params(CFG)
     rays = O.synthetic_rays(16, seed=3)
-    flat, n_in = _loss_and_grads(sd, rays, dp.shard_slice(16, rank, world), lambda n: dp.global_mean_weight(n, world))
+    # rank 1 passes the count as the engine keeps it in graph mode: a device-side int32 tensor (never read back to the host)
+    flat, n_in = _loss_and_grads(sd, rays, dp.shard_slice(16, rank, world),
+                                 lambda n: dp.global_mean_weight(torch.tensor([n], dtype=torch.int32) if rank else n, world))
     dp.sync_gradients(flat, world)
     if rank == 0:
         q.put(flat.numpy())
