@@ -13,12 +13,13 @@
 //   Round 2 (v3): every HBM operand of the epilogue moves through TMA.  The epilogue warps form TEAMS of four warps (one
 //   per TMEM lane quarter); a team works on [128 rows x 16 columns] units.  Per team a FIFO of 8 KB shared-memory slots
 //   (SWIZZLE_64B boxes, bank-conflict free for one-row-per-thread 16-byte accesses) is filled by cp.async.bulk.tensor
-//   loads that the team's leader thread issues up to kSlotsIn units AHEAD -- across units, layers and tiles, i.e. while
-//   the tensor core is still busy with the MMAs whose epilogue will consume them -- and results leave through
-//   cp.async.bulk.tensor stores from kSlotsOut staging slots.  No thread ever waits on a global load; the former
+//   loads that one lane of the aux-loader warp issues up to kSlotsIn entries AHEAD -- across units, layers and tiles, i.e.
+//   while the tensor core is still busy with the MMAs whose epilogue will consume them -- and results leave through
+//   cp.async.bulk.tensor stores that one lane of the store warp issues from kSlotsOut staging slots.  Shipped
+//   configuration: 4 teams (16 epilogue warps + MMA, W-loader, aux-loader and store warp = 640 threads).  No thread ever waits on a global load; the former
 //   long-scoreboard stalls (ncu, round 1: 6.6 of 12.3 cycles per issued instruction) are gone.
 //   Weights stream from L2 as pre-swizzled images: one stage = the hi and lo planes of one 64-wide K chunk for one
-//   half of the N range (32 KB, cp.async.bulk, 4-stage mbarrier ring).
+//   half of the N range (32 KB, cp.async.bulk, kWStages-deep mbarrier ring).
 //
 // This realises SURVEY.md K2/K3/K4/K10/K13 "activations stay on-chip across layers".
 //
@@ -80,7 +81,7 @@ struct ChainParamsDev {
 
 // ---------------------------------------------------------------------------------------------- configuration
 #ifndef NERO_TEAMS
-#define NERO_TEAMS 3
+#define NERO_TEAMS 4
 #endif
 #ifndef NERO_SLOTS_IN
 #define NERO_SLOTS_IN 2
@@ -94,7 +95,7 @@ constexpr int kChEpiWarps = 4 * kTeams;
 constexpr int kChMmaWarp = kChEpiWarps, kChLoadWarp = kChEpiWarps + 1, kChAuxWarp = kChEpiWarps + 2, kChStoreWarp = kChEpiWarps + 3;
 constexpr int kChThreads = (kChEpiWarps + 4) * 32;
 #ifndef NERO_WSTAGES
-#define NERO_WSTAGES 4
+#define NERO_WSTAGES 3
 #endif
 constexpr int kWStages = NERO_WSTAGES;
 // Timing experiments only (tools/bench_chain.py A/B builds; results are WRONG with any bit set): 1|2 = the MMA issuer and the
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(kChThreads, 1) umma_chain_kernel(const __grid_
         auto before_a_write = [&](int u) {
           if (u < 8 && !got_acc1 && !got_free) { if (!(kExp & 2)) mbar_wait(a_free, acc_phase); tcgen05_fence_after(); got_free = true; }
         };
-        const int u0 = (team + l) % kTeams;          // rotate the unit -> team assignment so the 16 = 6+5+5 split evens out
+        const int u0 = (team + l) % kTeams;          // rotate the unit -> team assignment (evens out an uneven split of the 16 units)
 #define NERO_EPI_CALL(K) epi_layer<K>(p, l, t, u0, tl, tile, rows_valid, tile_tma_ok, sb, before_unit, before_a_write)
         if constexpr ((kExp & 8) != 0) {
         } else if constexpr (FAM == 0) {
