@@ -10,7 +10,10 @@ sample_ray (64 coarse + 4x16 up-sampled + 32 background samples) + render_core f
 Three legs, all on THE SAME 1024 synthetic rays per GPU (nero_b200.synthetic.synthetic_rays, seed 6033):
   value   rays already resident in HBM, sample_ray/render_core called directly;
   e2e     through the public API `net({'step': s})`: the ray batch is fetched from the renderer's pinned host ray table
-          (H2D inside the timed region), the scalar loss is read back every step (train/trainer.py:168);
+          (H2D inside the timed region), the scalar loss is read back every step (train/trainer.py:168).  The headline leg
+          runs with cfg['cuda_graph'] (the step replayed from two captured graphs, nero_b200/graph.py); the eager leg and
+          both variants at the reference's default train_ray_num = 512 are reported under `e2e.eager` /
+          `e2e.train_ray_num_512`;
   bear    the same resident loop on BASELINE.json configs[2] (human light, 2048 rays on one GPU; 1024 per GPU under
           torchrun = configs[4] at 8 GPUs), reported under the key "bear" of the same JSON line.
 Prints ONE JSON line (see the driver contract in the task statement).
