@@ -83,6 +83,14 @@ void hc_human(int n, const float* p, const float* r, const float* pose, const fl
     }
   }
 }
+// sphere_direction: s = unit-sphere exit direction of the ray (p, d); gd = (ds/dd)^T gs
+void hc_sphere_dir(int n, const float* p, const float* d, const float* gs, float* s, float* gd) {
+  for (int i = 0; i < n; ++i) {
+    sphere_dir_fwd(p + 3 * i, d + 3 * i, s + 3 * i);
+    gd[3 * i] = gd[3 * i + 1] = gd[3 * i + 2] = 0.f;
+    sphere_dir_bwd(p + 3 * i, d + 3 * i, gs + 3 * i, gd + 3 * i);
+  }
+}
 void hc_srgb(int n, const float* x, float* y, float* dy) { for (int i = 0; i < n; ++i) { y[i] = linear_to_srgb(x[i]); dy[i] = dlinear_to_srgb(x[i]); } }
 // stage II: sampled direction, specular weight and Schlick factor of one (point, sample) with forward-mode d/d(roughness)
 void hc_mc(int n, const float* normal, const float* view, const float* a, const float* az01, const float* el, const int* spec, int ggx,

@@ -148,6 +148,27 @@ def test_geometry(hc):
     close(odg, Gd.grad, 1e-3, 1e-3, 'dg')
 
 
+def test_sphere_direction(hc):
+    """sphere_dir_fwd/bwd (math_shade.cuh) against offset_points_to_sphere + get_sphere_intersection + normalize
+    (network/field.py:380-396, 560-563) and their fp64 autograd w.r.t. the direction; points inside, near and outside the
+    0.999 sphere."""
+    torch.manual_seed(11)
+    n = 400
+    p = torch.randn(n, 3)
+    p = p / p.norm(dim=-1, keepdim=True) * torch.cat([torch.rand(n - 100) * 0.95, 0.99 + 0.03 * torch.rand(100)]).unsqueeze(-1)
+    d = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    gs = torch.randn(n, 3)
+    s_out, gd = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    hc.hc_sphere_dir(n, P(f32(p)), P(f32(d)), P(f32(gs)), P(s_out), P(gd))
+    sp = O.offset_points_to_sphere(p)
+    close(s_out, torch.nn.functional.normalize(sp + d * O.get_sphere_intersection(sp, d), dim=-1), 2e-5, 2e-6, 'sphere direction')
+    dd = d.double().requires_grad_(True)
+    spd = O.offset_points_to_sphere(p.double())
+    s64 = torch.nn.functional.normalize(spd + dd * O.get_sphere_intersection(spd, dd), dim=-1)
+    (s64 * gs.double()).sum().backward()
+    close(gd, dd.grad, 2e-4, 2e-5, 'd sphere direction / d dir')
+
+
 def test_combine(hc):
     g = torch.Generator().manual_seed(7)
     n = 600
